@@ -1,0 +1,134 @@
+"""Python face of the C-ABI (include/vilba.h): thin ctypes calls into libvilba.so.
+
+Every call here ends in the CUDA kernels of mc_slam_b200/csrc; if the library or a CUDA device is
+missing the constructor raises (there is no CPU path in the product).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import PREINT_DOUBLES, CResult, CWindow, Params, Result, Stats, Window, default_params
+
+
+class VilbaError(RuntimeError):
+    pass
+
+
+class Context:
+    """vilba_ctx: owns the CUDA stream, device arenas and the LM controller state of one caller thread."""
+
+    def __init__(self, device: int = 0, params: Optional[Params] = None):
+        self._lib = capi.load_library()
+        self.params = params or default_params()
+        self._h = self._lib.vilba_create(int(device), C.byref(self.params))
+        if not self._h:
+            raise VilbaError(
+                f"vilba_create(device={device}) failed: no usable CUDA device or kernels not loadable "
+                "(the VI local-BA path has no CPU fallback)"
+            )
+        self.device = int(device)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vilba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st: int, what: str):
+        if st < 0:
+            raise VilbaError(f"{what} failed ({st}): {self._lib.vilba_last_error(self._h).decode()}")
+
+    # ---- entry 1: Optimizer::LocalBundleAdjustmentNavState phases C..E ---------------------------
+    def local_ba(self, win: Window, stop_flag: Optional[np.ndarray] = None) -> Result:
+        res = Result.alloc(win)
+        cw, cr = win.as_c(), res.as_c()
+        sf = stop_flag.ctypes.data_as(C.POINTER(C.c_uint8)) if stop_flag is not None else None
+        st = self._lib.vilba_local_ba(self._h, C.byref(cw), C.byref(cr), sf)
+        self._check(st, "vilba_local_ba")
+        return res.take(cr)
+
+    def local_ba_batch(self, wins: Sequence[Window]) -> List[Result]:
+        n = len(wins)
+        results = [Result.alloc(w) for w in wins]
+        cws = (CWindow * n)(*[w.as_c() for w in wins])
+        crs = (CResult * n)(*[r.as_c() for r in results])
+        st = self._lib.vilba_local_ba_batch(self._h, n, cws, crs)
+        self._check(st, "vilba_local_ba_batch")
+        return [r.take(crs[i]) for i, r in enumerate(results)]
+
+    # ---- device-resident variant (bench: inputs already in HBM) ---------------------------------
+    def upload(self, win: Window):
+        self._keep = win
+        cw = win.as_c()
+        self._check(self._lib.vilba_window_upload(self._h, C.byref(cw)), "vilba_window_upload")
+
+    def solve_resident(self) -> Result:
+        res = Result(kf_state=np.zeros((0, 22)), pt_xyz=np.zeros((0, 3)), obs_outlier=np.zeros(0, np.uint8),
+                     obs_chi2=np.zeros(0))
+        cr = CResult()
+        st = self._lib.vilba_window_solve_resident(self._h, C.byref(cr))
+        self._check(st, "vilba_window_solve_resident")
+        return res.take(cr)
+
+    def download(self) -> Result:
+        res = Result.alloc(self._keep)
+        cr = res.as_c()
+        self._check(self._lib.vilba_window_download(self._h, C.byref(cr)), "vilba_window_download")
+        return res
+
+    # ---- entry 2: IMUPreintegrator::update loop, batched ----------------------------------------
+    def preintegrate_batch(self, sample_begin, gyro, acc, dt, bg, ba) -> np.ndarray:
+        sb = np.ascontiguousarray(sample_begin, dtype=np.int32)
+        n = sb.size - 1
+        g = np.ascontiguousarray(gyro, dtype=np.float64).reshape(-1)
+        a = np.ascontiguousarray(acc, dtype=np.float64).reshape(-1)
+        t = np.ascontiguousarray(dt, dtype=np.float64).reshape(-1)
+        b1 = np.ascontiguousarray(bg, dtype=np.float64).reshape(-1)
+        b2 = np.ascontiguousarray(ba, dtype=np.float64).reshape(-1)
+        if g.size != 3 * sb[-1] or a.size != g.size or t.size != sb[-1] or b1.size != 3 * n or b2.size != 3 * n:
+            raise ValueError("inconsistent IMU batch shapes")
+        out = np.zeros((n, PREINT_DOUBLES), np.float64)
+        dp = C.POINTER(C.c_double)
+        st = self._lib.vilba_preintegrate_batch(
+            self._h, n, sb.ctypes.data_as(C.POINTER(C.c_int32)), g.ctypes.data_as(dp), a.ctypes.data_as(dp),
+            t.ctypes.data_as(dp), b1.ctypes.data_as(dp), b2.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        self._check(st, "vilba_preintegrate_batch")
+        return out
+
+    def preintegrate_batch_dev(self, n_pairs: int, n_samples: int, sample_begin_ptr: int, gyro_ptr: int, acc_ptr: int,
+                               dt_ptr: int, bg_ptr: int, ba_ptr: int, out_ptr: int):
+        st = self._lib.vilba_preintegrate_batch_dev(self._h, n_pairs, n_samples, sample_begin_ptr, gyro_ptr, acc_ptr,
+                                                    dt_ptr, bg_ptr, ba_ptr, out_ptr)
+        self._check(st, "vilba_preintegrate_batch_dev")
+
+    # ---- introspection ---------------------------------------------------------------------------
+    def stats(self) -> Stats:
+        s = Stats()
+        self._lib.vilba_get_stats(self._h, C.byref(s))
+        return s
+
+    def reset_stats(self):
+        self._lib.vilba_reset_stats(self._h)
+
+    def set_profiling(self, on: bool):
+        self._lib.vilba_set_profiling(self._h, int(bool(on)))
+
+
+def version() -> str:
+    return capi.load_library().vilba_version().decode()

@@ -1,0 +1,109 @@
+// kernels.h -- device-side data layout and kernel launchers of the VI local-BA path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vilba.h"
+
+namespace vilba {
+
+constexpr int kPreintThreads = 256;
+constexpr int kPointThreads = 256;  // 8 warps per CTA, one warp per map point
+constexpr int kCholThreads = 1024;
+constexpr int kCholNB = 16;
+constexpr int kMaxKF = 256;          // key-frames per window supported by the shared-memory stage
+
+// obs record: 16 bytes, one vector load per mono edge.
+//   x = bits of float u, y = bits of float v, z = bits of float invSigma2,
+//   w = key-frame index (bits 0..23) | OBS_CULLED | OBS_ROBUST
+constexpr int OBS_KF_MASK = 0x00ffffff;
+constexpr int OBS_CULLED = 1 << 24;  // e->setLevel(1)            (Optimizer.cpp:2667-2670)
+constexpr int OBS_ROBUST = 1 << 25;  // edge still has its Huber  (Optimizer.cpp:2672)
+
+// Device-resident Levenberg-Marquardt controller state
+// (members of OptimizationAlgorithmLevenberg, optimization_algorithm_levenberg.cpp:41-60)
+struct LmState {
+    double lambda;        // _currentLambda
+    double ni;            // _ni
+    double current_chi;   // currentChi
+    double ini_chi;       // iniChi
+    double temp_chi;      // tempChi
+    double rho;
+    double lambda_first;  // lambda used by the first trial of this iteration (trace)
+    double chi_acc;       // accumulator: robust chi2 of the state being evaluated
+    double scale_acc;     // accumulator: sum_j x_j (lambda x_j + b_j) over landmarks
+    unsigned long long maxdiag_bits;  // max |diag(H_ll)| as ordered bits (non-negative doubles)
+    int cur;              // which of the two estimate buffers holds the current state
+    int chol_fail;        // non-positive pivot in the reduced system
+    int qmax;             // _levenbergIterations
+    int n_bad;            // _nBad
+    int accepted;         // last trial accepted
+    int iter_result;      // -1 running, 0 OK, 1 Terminate
+    int stop;             // force-stop flag mirrored from the host
+    int pad;
+};
+
+struct DevWindow {
+    int K, NI, P, E, n_free, n;  // n = 15 * n_free
+    // estimates, double buffered (index LmState::cur = accepted state, 1-cur = trial state)
+    double* kf_state[2];  // K * 22
+    double* pts[2];       // P * 3
+    const int* kf_block;  // K: block index among free key-frames, -1 if fixed
+    // imu edges
+    const int* imu_i;
+    const int* imu_j;
+    const double* imu_preint;  // NI * 142
+    double* imu_info;          // NI * 81   inverse of cov_P_V_Phi
+    double* imu_err;           // NI * 15   cached _error of (PVR 9, Bias 6)
+    // mono edges, CSR by point
+    const int* pt_obs_begin;  // P + 1
+    int4* obs;                // E records
+    double* obs_chi2;         // E: e->chi2() of the last evaluation that had the edge active
+    // normal equations
+    double* Hpp;  // n * n   upper block triangle + full diagonal blocks
+    double* bp;   // n
+    double* Hll;  // P * 6   (xx,xy,xz,yy,yz,zz)
+    double* bl;   // P * 3
+    double* W;    // E * 18  H_pl block of the edge, 6x3 rows [P,Phi]
+    double* S;    // n * n   reduced camera system (upper triangle used)
+    double* bs;   // n
+    double* x;    // n       pose increment
+    LmState* lm;
+    // calibration (g2otypes.h:686-705)
+    double fx, fy, cx, cy;
+    double Rcb[9];  // Rbc^T
+    double tcb[3];  // -Rcb * Pbc
+    double g[3];
+    // parameters
+    double huber_mono, huber_pvr, huber_bias, chi2_gate;
+    double inv_gyr_rw2, inv_acc_rw2;
+    double lm_tau, lm_good_lo, lm_good_hi;
+    int max_trials;
+};
+
+// ---- K1 ------------------------------------------------------------------------------------------
+size_t preint_smem_bytes(int group);
+cudaError_t launch_preint_batch(cudaStream_t stream, int n_pairs, const int* sample_begin, const double* gyro,
+                                const double* acc, const double* dt, const double* bg, const double* ba,
+                                double* out, double gyr_cov, double acc_cov, int group);
+
+// ---- local BA ------------------------------------------------------------------------------------
+struct LaunchCfg {
+    int point_grid;   // CTAs of the per-point kernels
+    int sm_count;
+};
+
+cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow& w);
+// evaluate (and optionally first apply x to) the estimates; accumulates robust chi2 into lm->chi_acc
+cudaError_t launch_update_eval(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, bool apply);
+cudaError_t launch_linearize(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
+cudaError_t launch_schur(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
+cudaError_t launch_chol_solve(cudaStream_t s, const DevWindow& w);
+// LM bookkeeping kernels (single CTA)
+cudaError_t launch_lm_stage_begin(cudaStream_t s, const DevWindow& w);   // current_chi = chi_acc
+cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow& w, int iteration);
+cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow& w);
+cudaError_t launch_cull(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, int* n_culled_dev);
+cudaError_t launch_final_flags(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, uint8_t* outlier);
+
+}  // namespace vilba

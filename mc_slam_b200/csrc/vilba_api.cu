@@ -1,0 +1,650 @@
+// vilba_api.cu -- host C++ controller + the extern "C" boundary declared in include/vilba.h.
+//
+// The host side mirrors the control flow of Optimizer::LocalBundleAdjustmentNavState phases C..E
+// (src/Optimizer.cpp:2643-2701) and of SparseOptimizer::optimize / OptimizationAlgorithmLevenberg::solve
+// (g2o/core/sparse_optimizer.cpp:354-419, optimization_algorithm_levenberg.cpp:61-164); all arithmetic
+// runs in the CUDA kernels of lba_kernels.cu / preint.cu.  There is no CPU fallback: without a usable
+// CUDA device vilba_create() returns NULL.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace vilba;
+
+namespace {
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + (1u << 20);
+        cudaError_t e = cudaMalloc(&base, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = 0;
+    }
+};
+
+struct Pinned {
+    char* base = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + (1u << 16);
+        cudaError_t e = cudaMallocHost(&base, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+        cap = 0;
+    }
+};
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// offsets of one window inside the device arena
+struct Layout {
+    // input section (one H2D copy)
+    size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, input_end;
+    // work section
+    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, S, bs, x, lm, n_culled,
+        outlier, total;
+};
+
+Layout make_layout(int K, int NI, int P, int E, int n) {
+    Layout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes);
+        return at;
+    };
+    L.kf_state0 = take(sizeof(double) * 22 * (size_t)K);
+    L.pts0 = take(sizeof(double) * 3 * (size_t)P);
+    L.imu_preint = take(sizeof(double) * 142 * (size_t)NI);
+    L.obs0 = take(sizeof(int4) * (size_t)E);
+    L.pt_obs_begin = take(sizeof(int) * ((size_t)P + 1));
+    L.kf_block = take(sizeof(int) * (size_t)K);
+    L.imu_i = take(sizeof(int) * (size_t)NI);
+    L.imu_j = take(sizeof(int) * (size_t)NI);
+    L.input_end = o;
+    for (int b = 0; b < 2; ++b) L.kf_state[b] = take(sizeof(double) * 22 * (size_t)K);
+    for (int b = 0; b < 2; ++b) L.pts[b] = take(sizeof(double) * 3 * (size_t)P);
+    L.imu_info = take(sizeof(double) * 81 * (size_t)NI);
+    L.imu_err = take(sizeof(double) * 15 * (size_t)NI);
+    L.obs = take(sizeof(int4) * (size_t)E);
+    L.obs_chi2 = take(sizeof(double) * (size_t)E);
+    L.Hpp = take(sizeof(double) * (size_t)n * n);
+    L.bp = take(sizeof(double) * (size_t)n);
+    L.Hll = take(sizeof(double) * 6 * (size_t)P);
+    L.bl = take(sizeof(double) * 3 * (size_t)P);
+    L.W = take(sizeof(double) * 18 * (size_t)E);
+    L.S = take(sizeof(double) * (size_t)n * n);
+    L.bs = take(sizeof(double) * (size_t)n);
+    L.x = take(sizeof(double) * (size_t)n);
+    L.lm = take(sizeof(LmState));
+    L.n_culled = take(sizeof(int) * 4);
+    L.outlier = take((size_t)E);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+struct vilba_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    vilba_params prm;
+    Arena arena, preint_arena;
+    Pinned pinned, pinned_small;
+    std::string err;
+    int sm_count = 148;
+    // resident window
+    bool has_window = false;
+    Layout L;
+    DevWindow dw;
+    LaunchCfg cfg;
+    int win_E = 0, win_NI = 0, win_P = 0, win_K = 0;
+    // stats
+    vilba_stats stats;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs, drained at sync points
+    std::vector<int> prof_kind;
+    size_t prof_used = 0;
+};
+
+namespace {
+
+bool fail(vilba_ctx* c, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return false;
+    c->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return true;
+}
+
+#define CK(call, what)                          \
+    do {                                        \
+        if (fail(ctx, (call), what)) return VILBA_ERR_CUDA; \
+    } while (0)
+
+int check_window(const vilba_window* w) {
+    if (!w || w->n_kf <= 0 || w->n_imu < 0 || w->n_pts < 0 || w->n_obs < 0) return VILBA_ERR_ARG;
+    if (w->n_kf > (OBS_KF_MASK) || w->n_kf > kMaxKF) return VILBA_ERR_ARG;
+    if (!w->kf_state || !w->kf_flags) return VILBA_ERR_ARG;
+    if (w->n_imu && (!w->imu_kf_i || !w->imu_kf_j || !w->imu_preint)) return VILBA_ERR_ARG;
+    if (w->n_pts && (!w->pt_xyz || !w->pt_obs_begin)) return VILBA_ERR_ARG;
+    if (w->n_obs && (!w->obs_kf || !w->obs_uv || !w->obs_inv_sigma2)) return VILBA_ERR_ARG;
+    int n_free = 0;
+    for (int k = 0; k < w->n_kf; ++k) {
+        const bool fixed = (w->kf_flags[k] & VILBA_KF_FIXED) != 0;
+        if (!fixed && !(w->kf_flags[k] & VILBA_KF_HAS_BIAS)) return VILBA_ERR_ARG;
+        n_free += fixed ? 0 : 1;
+    }
+    if (n_free == 0) return VILBA_ERR_ARG;
+    for (int e = 0; e < w->n_imu; ++e) {
+        const int i = w->imu_kf_i[e], j = w->imu_kf_j[e];
+        if (i < 0 || j < 0 || i >= w->n_kf || j >= w->n_kf) return VILBA_ERR_ARG;
+        if (!(w->kf_flags[i] & VILBA_KF_HAS_BIAS) || !(w->kf_flags[j] & VILBA_KF_HAS_BIAS)) return VILBA_ERR_ARG;
+    }
+    if (w->n_pts && (w->pt_obs_begin[0] != 0 || w->pt_obs_begin[w->n_pts] != w->n_obs)) return VILBA_ERR_ARG;
+    for (int e = 0; e < w->n_obs; ++e)
+        if (w->obs_kf[e] < 0 || w->obs_kf[e] >= w->n_kf) return VILBA_ERR_ARG;
+    return VILBA_OK;
+}
+
+// profiling helpers: an event pair around one launch group, tagged by kind (0 linearize, 1 schur, 2 solve)
+void prof_begin(vilba_ctx* ctx, int kind) {
+    if (!ctx->profiling) return;
+    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ctx->prof_events.push_back(e);
+        }
+        ctx->prof_kind.push_back(kind);
+    }
+    ctx->prof_kind[ctx->prof_used / 2] = kind;
+    cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream);
+}
+void prof_end(vilba_ctx* ctx) {
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream);
+    ctx->prof_used += 2;
+}
+void prof_drain(vilba_ctx* ctx) {  // call after a stream synchronize
+    for (size_t i = 0; i < ctx->prof_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]) != cudaSuccess) continue;
+        switch (ctx->prof_kind[i / 2]) {
+            case 0: ctx->stats.linearize_ms += ms; ctx->stats.linearize_launches++; break;
+            case 1: ctx->stats.schur_ms += ms; ctx->stats.schur_launches++; break;
+            default: ctx->stats.solve_ms += ms; ctx->stats.solve_launches++; break;
+        }
+    }
+    ctx->prof_used = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flatten + upload: phase A/B of the reference function become "pack into pinned memory, one H2D"
+// ------------------------------------------------------------------------------------------------
+int upload_window(vilba_ctx* ctx, const vilba_window* w) {
+    int st = check_window(w);
+    if (st != VILBA_OK) {
+        ctx->err = "invalid window";
+        return st;
+    }
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const int K = w->n_kf, NI = w->n_imu, P = w->n_pts, E = w->n_obs;
+    std::vector<int> kf_block(K, -1);
+    int n_free = 0;
+    for (int k = 0; k < K; ++k)
+        if (!(w->kf_flags[k] & VILBA_KF_FIXED)) kf_block[k] = n_free++;
+    const int n = 15 * n_free;
+    const Layout L = make_layout(K, NI, P, E, n);
+    CK(ctx->arena.reserve(L.total), "cudaMalloc(arena)");
+    CK(ctx->pinned.reserve(L.input_end), "cudaMallocHost(staging)");
+    char* h = ctx->pinned.base;
+    std::memcpy(h + L.kf_state0, w->kf_state, sizeof(double) * 22 * (size_t)K);
+    if (P) std::memcpy(h + L.pts0, w->pt_xyz, sizeof(double) * 3 * (size_t)P);
+    if (NI) std::memcpy(h + L.imu_preint, w->imu_preint, sizeof(double) * 142 * (size_t)NI);
+    int4* ho = reinterpret_cast<int4*>(h + L.obs0);
+    for (int e = 0; e < E; ++e) {
+        int4 r;
+        std::memcpy(&r.x, &w->obs_uv[2 * (size_t)e], 4);
+        std::memcpy(&r.y, &w->obs_uv[2 * (size_t)e + 1], 4);
+        std::memcpy(&r.z, &w->obs_inv_sigma2[e], 4);
+        r.w = w->obs_kf[e] | OBS_ROBUST;  // every mono edge starts with its Huber kernel (Optimizer.cpp:2622-2624)
+        ho[e] = r;
+    }
+    if (P) std::memcpy(h + L.pt_obs_begin, w->pt_obs_begin, sizeof(int) * ((size_t)P + 1));
+    else std::memset(h + L.pt_obs_begin, 0, sizeof(int));
+    std::memcpy(h + L.kf_block, kf_block.data(), sizeof(int) * (size_t)K);
+    if (NI) {
+        std::memcpy(h + L.imu_i, w->imu_kf_i, sizeof(int) * (size_t)NI);
+        std::memcpy(h + L.imu_j, w->imu_kf_j, sizeof(int) * (size_t)NI);
+    }
+    char* d = ctx->arena.base;
+    CK(cudaMemcpyAsync(d, h, L.input_end, cudaMemcpyHostToDevice, ctx->stream), "H2D window");
+
+    DevWindow& dw = ctx->dw;
+    std::memset(&dw, 0, sizeof(dw));
+    dw.K = K, dw.NI = NI, dw.P = P, dw.E = E, dw.n_free = n_free, dw.n = n;
+    for (int b = 0; b < 2; ++b) {
+        dw.kf_state[b] = reinterpret_cast<double*>(d + L.kf_state[b]);
+        dw.pts[b] = reinterpret_cast<double*>(d + L.pts[b]);
+    }
+    dw.kf_block = reinterpret_cast<const int*>(d + L.kf_block);
+    dw.imu_i = reinterpret_cast<const int*>(d + L.imu_i);
+    dw.imu_j = reinterpret_cast<const int*>(d + L.imu_j);
+    dw.imu_preint = reinterpret_cast<const double*>(d + L.imu_preint);
+    dw.imu_info = reinterpret_cast<double*>(d + L.imu_info);
+    dw.imu_err = reinterpret_cast<double*>(d + L.imu_err);
+    dw.pt_obs_begin = reinterpret_cast<const int*>(d + L.pt_obs_begin);
+    dw.obs = reinterpret_cast<int4*>(d + L.obs);
+    dw.obs_chi2 = reinterpret_cast<double*>(d + L.obs_chi2);
+    dw.Hpp = reinterpret_cast<double*>(d + L.Hpp);
+    dw.bp = reinterpret_cast<double*>(d + L.bp);
+    dw.Hll = reinterpret_cast<double*>(d + L.Hll);
+    dw.bl = reinterpret_cast<double*>(d + L.bl);
+    dw.W = reinterpret_cast<double*>(d + L.W);
+    dw.S = reinterpret_cast<double*>(d + L.S);
+    dw.bs = reinterpret_cast<double*>(d + L.bs);
+    dw.x = reinterpret_cast<double*>(d + L.x);
+    dw.lm = reinterpret_cast<LmState*>(d + L.lm);
+    dw.fx = w->fx, dw.fy = w->fy, dw.cx = w->cx, dw.cy = w->cy;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) dw.Rcb[3 * r + c] = w->Rbc[3 * c + r];  // Rcb = Rbc^T
+    for (int r = 0; r < 3; ++r) {  // tcb = -(Rcb * Pbc)
+        double s = 0.0;
+        for (int c = 0; c < 3; ++c) s += dw.Rcb[3 * r + c] * w->Pbc[c];
+        dw.tcb[r] = -s;
+    }
+    for (int i = 0; i < 3; ++i) dw.g[i] = w->gravity[i];
+    const vilba_params& p = ctx->prm;
+    dw.huber_mono = p.huber_mono, dw.huber_pvr = p.huber_pvr, dw.huber_bias = p.huber_bias;
+    dw.chi2_gate = p.chi2_gate;
+    dw.inv_gyr_rw2 = 1.0 / p.gyr_bias_rw2, dw.inv_acc_rw2 = 1.0 / p.acc_bias_rw2;
+    dw.lm_tau = p.lm_tau, dw.lm_good_lo = p.lm_good_lo, dw.lm_good_hi = p.lm_good_hi;
+    dw.max_trials = p.max_trials;
+
+    ctx->L = L;
+    ctx->win_E = E, ctx->win_NI = NI, ctx->win_P = P, ctx->win_K = K;
+    const int warps_per_cta = kPointThreads / 32;
+    int grid = (P + NI + warps_per_cta - 1) / warps_per_cta;
+    const int cap = ctx->sm_count * 8;  // <= 8 resident CTAs of 256 threads per SM
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    ctx->cfg.point_grid = grid;
+    ctx->cfg.sm_count = ctx->sm_count;
+    ctx->has_window = true;
+    return VILBA_OK;
+}
+
+// restart from the uploaded initial state (device-to-device)
+int reset_window(vilba_ctx* ctx) {
+    const Layout& L = ctx->L;
+    char* d = ctx->arena.base;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(d + L.kf_state[0], d + L.kf_state0, sizeof(double) * 22 * (size_t)ctx->win_K,
+                       cudaMemcpyDeviceToDevice, s), "reset kf");
+    CK(cudaMemcpyAsync(d + L.kf_state[1], d + L.kf_state0, sizeof(double) * 22 * (size_t)ctx->win_K,
+                       cudaMemcpyDeviceToDevice, s), "reset kf");
+    if (ctx->win_P) {
+        CK(cudaMemcpyAsync(d + L.pts[0], d + L.pts0, sizeof(double) * 3 * (size_t)ctx->win_P,
+                           cudaMemcpyDeviceToDevice, s), "reset pts");
+        CK(cudaMemcpyAsync(d + L.pts[1], d + L.pts0, sizeof(double) * 3 * (size_t)ctx->win_P,
+                           cudaMemcpyDeviceToDevice, s), "reset pts");
+    }
+    if (ctx->win_E) {
+        CK(cudaMemcpyAsync(d + L.obs, d + L.obs0, sizeof(int4) * (size_t)ctx->win_E, cudaMemcpyDeviceToDevice, s),
+           "reset obs");
+        CK(cudaMemsetAsync(d + L.obs_chi2, 0, sizeof(double) * (size_t)ctx->win_E, s), "reset chi2");
+    }
+    CK(cudaMemsetAsync(d + L.lm, 0, sizeof(LmState), s), "reset lm");
+    CK(cudaMemsetAsync(d + L.n_culled, 0, sizeof(int) * 4, s), "reset counters");
+    return VILBA_OK;
+}
+
+int read_lm(vilba_ctx* ctx, LmState* out) {
+    CK(ctx->pinned_small.reserve(sizeof(LmState) + 64), "cudaMallocHost(lm)");
+    CK(cudaMemcpyAsync(ctx->pinned_small.base, ctx->dw.lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream),
+       "D2H lm");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    std::memcpy(out, ctx->pinned_small.base, sizeof(LmState));
+    prof_drain(ctx);
+    return VILBA_OK;
+}
+
+bool stop_requested(const volatile uint8_t* f) { return f && *f; }
+
+// SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg (sparse_optimizer.cpp:354-419)
+int run_stage(vilba_ctx* ctx, int stage, int iterations, int n_active, vilba_result* out,
+              const volatile uint8_t* stop_flag) {
+    const DevWindow& dw = ctx->dw;
+    cudaStream_t s = ctx->stream;
+    vilba_stats& stt = ctx->stats;
+    // computeActiveErrors + activeRobustChi2 at the first iteration; later iterations inherit currentChi
+    // of the accepted trial (identical by construction: the errors are those of the accepted state)
+    CK(launch_update_eval(s, dw, ctx->cfg, false), "eval");
+    CK(launch_lm_stage_begin(s, dw), "lm_stage_begin");
+    stt.kernel_launches += 2;
+    bool ok = true;
+    for (int it = 0; it < iterations && !stop_requested(stop_flag) && ok; ++it) {
+        prof_begin(ctx, 0);
+        CK(launch_linearize(s, dw, ctx->cfg), "linearize");
+        prof_end(ctx);
+        CK(launch_lm_iter_begin(s, dw, it), "lm_iter_begin");
+        stt.kernel_launches += 2 + (dw.NI > 0 ? 1 : 0);
+        stt.edges_linearized += n_active;
+        LmState lm;
+        do {
+            prof_begin(ctx, 1);
+            CK(launch_schur(s, dw, ctx->cfg), "schur");
+            prof_end(ctx);
+            prof_begin(ctx, 2);
+            CK(launch_chol_solve(s, dw), "chol");
+            prof_end(ctx);
+            CK(launch_update_eval(s, dw, ctx->cfg, true), "update_eval");
+            if (stop_requested(stop_flag)) {
+                const int one = 1;
+                CK(cudaMemcpyAsync(&dw.lm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, s), "stop");
+            }
+            CK(launch_lm_decide(s, dw), "lm_decide");
+            stt.kernel_launches += 5;
+            stt.lm_trials++;
+            int r = read_lm(ctx, &lm);
+            if (r != VILBA_OK) return r;
+        } while (lm.iter_result == -1);
+        stt.lm_iterations++;
+        if (out->n_trace < VILBA_MAX_TRACE) {
+            vilba_iter_record& rec = out->trace[out->n_trace++];
+            rec.stage = stage;
+            rec.iteration = it;
+            rec.trials = lm.qmax;
+            rec.result = lm.iter_result;
+            rec.n_active_edges = n_active;
+            rec.accepted = lm.accepted;
+            rec.chi2_initial = lm.ini_chi;
+            rec.chi2_final = lm.current_chi;
+            rec.lambda = lm.lambda;
+            rec.lambda_first_trial = lm.lambda_first;
+        }
+        ok = (lm.iter_result == 0);
+    }
+    return VILBA_OK;
+}
+
+int solve_resident(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_flag) {
+    if (!ctx->has_window) {
+        ctx->err = "no window uploaded";
+        return VILBA_ERR_ARG;
+    }
+    out->n_trace = 0;
+    out->stage2_ran = 0;
+    out->n_outliers_stage1 = 0;
+    out->solve_ms = 0.0;
+    out->status = VILBA_OK;
+    if (stop_requested(stop_flag)) {  // Optimizer.cpp:2643-2645
+        out->status = VILBA_ABORTED;
+        return VILBA_ABORTED;
+    }
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const DevWindow& dw = ctx->dw;
+    cudaStream_t s = ctx->stream;
+    int r = reset_window(ctx);
+    if (r != VILBA_OK) return r;
+    CK(cudaEventRecord(ctx->ev_a, s), "event");
+    CK(launch_imu_prepare(s, dw), "imu_prepare");
+    ctx->stats.kernel_launches += dw.NI > 0 ? 1 : 0;
+    const int n_all = dw.E + 2 * dw.NI;
+    r = run_stage(ctx, 1, ctx->prm.iters_stage1, n_all, out, stop_flag);
+    if (r != VILBA_OK) return r;
+    if (!stop_requested(stop_flag)) {  // bDoMore (Optimizer.cpp:2650-2656)
+        int* n_culled_dev = reinterpret_cast<int*>(ctx->arena.base + ctx->L.n_culled);
+        CK(launch_cull(s, dw, ctx->cfg, n_culled_dev), "cull");
+        ctx->stats.kernel_launches += 1;
+        CK(ctx->pinned_small.reserve(sizeof(LmState) + 64), "cudaMallocHost");
+        CK(cudaMemcpyAsync(ctx->pinned_small.base, n_culled_dev, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H");
+        CK(cudaStreamSynchronize(s), "sync");
+        int n_culled = 0;
+        std::memcpy(&n_culled, ctx->pinned_small.base, sizeof(int));
+        out->n_outliers_stage1 = n_culled;
+        r = run_stage(ctx, 2, ctx->prm.iters_stage2, n_all - n_culled, out, stop_flag);
+        if (r != VILBA_OK) return r;
+        out->stage2_ran = 1;
+    }
+    uint8_t* outl = reinterpret_cast<uint8_t*>(ctx->arena.base + ctx->L.outlier);
+    CK(launch_final_flags(s, dw, ctx->cfg, outl), "final_flags");
+    ctx->stats.kernel_launches += 1;
+    CK(cudaEventRecord(ctx->ev_b, s), "event");
+    CK(cudaStreamSynchronize(s), "sync");
+    prof_drain(ctx);
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b), "elapsed");
+    out->solve_ms = ms;
+    return VILBA_OK;
+}
+
+int download_window(vilba_ctx* ctx, vilba_result* out) {
+    if (!ctx->has_window) return VILBA_ERR_ARG;
+    LmState lm;
+    int r = read_lm(ctx, &lm);
+    if (r != VILBA_OK) return r;
+    const Layout& L = ctx->L;
+    char* d = ctx->arena.base;
+    cudaStream_t s = ctx->stream;
+    if (out->kf_state)
+        CK(cudaMemcpyAsync(out->kf_state, d + L.kf_state[lm.cur], sizeof(double) * 22 * (size_t)ctx->win_K,
+                           cudaMemcpyDeviceToHost, s), "D2H kf");
+    if (out->pt_xyz && ctx->win_P)
+        CK(cudaMemcpyAsync(out->pt_xyz, d + L.pts[lm.cur], sizeof(double) * 3 * (size_t)ctx->win_P,
+                           cudaMemcpyDeviceToHost, s), "D2H pts");
+    if (out->obs_outlier && ctx->win_E)
+        CK(cudaMemcpyAsync(out->obs_outlier, d + L.outlier, (size_t)ctx->win_E, cudaMemcpyDeviceToHost, s),
+           "D2H outlier");
+    if (out->obs_chi2 && ctx->win_E)
+        CK(cudaMemcpyAsync(out->obs_chi2, d + L.obs_chi2, sizeof(double) * (size_t)ctx->win_E,
+                           cudaMemcpyDeviceToHost, s), "D2H chi2");
+    CK(cudaStreamSynchronize(s), "sync");
+    return VILBA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+void vilba_default_params(vilba_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->iters_stage1 = 5;
+    p->iters_stage2 = 10;
+    p->max_trials = 10;
+    p->huber_mono = (double)(float)std::sqrt(5.991);
+    p->huber_pvr = (double)(float)std::sqrt(100 * 21.666);
+    p->huber_bias = (double)(float)std::sqrt(100 * 16.812);
+    p->chi2_gate = 5.991;
+    p->lm_tau = 1e-5;
+    p->lm_good_lo = 1. / 3.;
+    p->lm_good_hi = 2. / 3.;
+    p->gyr_bias_rw2 = 2.0e-5 * 2.0e-5;
+    p->acc_bias_rw2 = 5.0e-3 * 5.0e-3;
+    p->gyr_meas_cov = 1.7e-4 * 1.7e-4 / 0.005;
+    p->acc_meas_cov = 2.0e-3 * 2.0e-3 / 0.005 * 100;
+}
+
+const char* vilba_version(void) { return "vilba 0.1 (sm_100a, FP64)"; }
+
+vilba_ctx* vilba_create(int device, const vilba_params* params) {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
+        std::fprintf(stderr, "vilba_create: no usable CUDA device %d (found %d); there is no CPU fallback\n", device,
+                     n_dev);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    vilba_ctx* ctx = new vilba_ctx();
+    ctx->device = device;
+    if (params)
+        ctx->prm = *params;
+    else
+        vilba_default_params(&ctx->prm);
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
+        std::fprintf(stderr, "vilba_create: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return nullptr;
+    }
+    return ctx;
+}
+
+void vilba_destroy(vilba_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->arena.release();
+    ctx->preint_arena.release();
+    ctx->pinned.release();
+    ctx->pinned_small.release();
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* vilba_last_error(const vilba_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vilba_window_upload(vilba_ctx* ctx, const vilba_window* win) {
+    if (!ctx) return VILBA_ERR_ARG;
+    return upload_window(ctx, win);
+}
+
+int vilba_window_solve_resident(vilba_ctx* ctx, vilba_result* out) {
+    if (!ctx || !out) return VILBA_ERR_ARG;
+    int r = solve_resident(ctx, out, nullptr);
+    out->status = r;
+    return r;
+}
+
+int vilba_window_download(vilba_ctx* ctx, vilba_result* out) {
+    if (!ctx || !out) return VILBA_ERR_ARG;
+    return download_window(ctx, out);
+}
+
+int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, const volatile uint8_t* stop_flag) {
+    if (!ctx || !out) return VILBA_ERR_ARG;
+    out->n_trace = 0;
+    out->stage2_ran = 0;
+    out->n_outliers_stage1 = 0;
+    out->solve_ms = 0.0;
+    if (stop_flag && *stop_flag) {  // silent early return, nothing written (Optimizer.cpp:2643-2645)
+        out->status = VILBA_ABORTED;
+        return VILBA_ABORTED;
+    }
+    int r = upload_window(ctx, win);
+    if (r == VILBA_OK) r = solve_resident(ctx, out, stop_flag);
+    if (r == VILBA_OK) r = download_window(ctx, out);
+    out->status = r;
+    return r;
+}
+
+int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win, vilba_result* out) {
+    if (!ctx || n_windows < 0 || (n_windows && (!win || !out))) return VILBA_ERR_ARG;
+    int worst = VILBA_OK;
+    for (int i = 0; i < n_windows; ++i) {
+        int r = vilba_local_ba(ctx, &win[i], &out[i], nullptr);
+        if (r < 0) worst = r;
+    }
+    return worst;
+}
+
+int vilba_preintegrate_batch_dev(vilba_ctx* ctx, int32_t n_pairs, int32_t n_samples, const int32_t* sample_begin_dev,
+                                 const double* gyro_dev, const double* acc_dev, const double* dt_dev,
+                                 const double* bg_dev, const double* ba_dev, double* out_dev) {
+    if (!ctx || n_pairs < 0) return VILBA_ERR_ARG;
+    (void)n_samples;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(launch_preint_batch(ctx->stream, n_pairs, sample_begin_dev, gyro_dev, acc_dev, dt_dev, bg_dev, ba_dev, out_dev,
+                           ctx->prm.gyr_meas_cov, ctx->prm.acc_meas_cov, 8), "preint_batch");
+    ctx->stats.kernel_launches += n_pairs > 0 ? 1 : 0;
+    return VILBA_OK;
+}
+
+int vilba_preintegrate_batch(vilba_ctx* ctx, int32_t n_pairs, const int32_t* sample_begin, const double* gyro,
+                             const double* acc, const double* dt, const double* bg, const double* ba, double* out) {
+    if (!ctx || n_pairs < 0) return VILBA_ERR_ARG;
+    if (n_pairs == 0) return VILBA_OK;
+    if (!sample_begin || !gyro || !acc || !dt || !bg || !ba || !out) return VILBA_ERR_ARG;
+    for (int p = 0; p < n_pairs; ++p)
+        if (sample_begin[p + 1] < sample_begin[p]) return VILBA_ERR_ARG;
+    if (sample_begin[0] != 0) return VILBA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t ns = (size_t)sample_begin[n_pairs];
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes);
+        return at;
+    };
+    const size_t o_sb = take(sizeof(int) * ((size_t)n_pairs + 1));
+    const size_t o_g = take(sizeof(double) * 3 * ns), o_a = take(sizeof(double) * 3 * ns), o_t = take(sizeof(double) * ns);
+    const size_t o_bg = take(sizeof(double) * 3 * (size_t)n_pairs), o_ba = take(sizeof(double) * 3 * (size_t)n_pairs);
+    const size_t in_end = o;
+    const size_t o_out = take(sizeof(double) * 142 * (size_t)n_pairs);
+    CK(ctx->preint_arena.reserve(o), "cudaMalloc(preint)");
+    CK(ctx->pinned.reserve(in_end > sizeof(double) * 142 * (size_t)n_pairs ? in_end : sizeof(double) * 142 * (size_t)n_pairs),
+       "cudaMallocHost(preint)");
+    char* h = ctx->pinned.base;
+    std::memcpy(h + o_sb, sample_begin, sizeof(int) * ((size_t)n_pairs + 1));
+    std::memcpy(h + o_g, gyro, sizeof(double) * 3 * ns);
+    std::memcpy(h + o_a, acc, sizeof(double) * 3 * ns);
+    std::memcpy(h + o_t, dt, sizeof(double) * ns);
+    std::memcpy(h + o_bg, bg, sizeof(double) * 3 * (size_t)n_pairs);
+    std::memcpy(h + o_ba, ba, sizeof(double) * 3 * (size_t)n_pairs);
+    char* d = ctx->preint_arena.base;
+    CK(cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, ctx->stream), "H2D preint");
+    int r = vilba_preintegrate_batch_dev(ctx, n_pairs, (int)ns, reinterpret_cast<const int*>(d + o_sb),
+                                         reinterpret_cast<const double*>(d + o_g), reinterpret_cast<const double*>(d + o_a),
+                                         reinterpret_cast<const double*>(d + o_t), reinterpret_cast<const double*>(d + o_bg),
+                                         reinterpret_cast<const double*>(d + o_ba), reinterpret_cast<double*>(d + o_out));
+    if (r != VILBA_OK) return r;
+    CK(cudaMemcpyAsync(h, d + o_out, sizeof(double) * 142 * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream),
+       "D2H preint");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    std::memcpy(out, h, sizeof(double) * 142 * (size_t)n_pairs);
+    return VILBA_OK;
+}
+
+void vilba_get_stats(const vilba_ctx* ctx, vilba_stats* s) {
+    if (ctx && s) *s = ctx->stats;
+}
+void vilba_reset_stats(vilba_ctx* ctx) {
+    if (ctx) std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+}
+void vilba_set_profiling(vilba_ctx* ctx, int on) {
+    if (ctx) ctx->profiling = on != 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""T4/T5: the CUDA path, called through the C ABI, against the CPU oracle on identical windows.
+
+Tolerances (BASELINE.json north_star): per-iteration chi2 relative error <= 1e-6, final pose/point
+deltas <= 1e-5, identical accept/reject sequence and identical outlier set."""
+import numpy as np
+import pytest
+
+from mc_slam_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(vilba):
+    c = vilba.Context(0)
+    yield c
+    c.close()
+
+
+def _compare(r, o, w, chi_rtol=1e-6, state_atol=1e-5):
+    assert r.status == o.status == 0
+    assert r.stage2_ran == o.stage2_ran
+    assert r.n_outliers_stage1 == o.n_outliers_stage1
+    assert len(r.trace) == len(o.trace)
+    for a, b in zip(r.trace, o.trace):
+        assert (a["stage"], a["iteration"], a["trials"], a["accepted"], a["result"], a["n_active_edges"]) == (
+            b["stage"], b["iteration"], b["trials"], b["accepted"], b["result"], b["n_active_edges"])
+        assert abs(a["chi2_initial"] - b["chi2_initial"]) <= chi_rtol * abs(b["chi2_initial"])
+        assert abs(a["chi2_final"] - b["chi2_final"]) <= chi_rtol * abs(b["chi2_final"])
+        assert abs(a["lambda_"] - b["lambda_"]) <= 1e-6 * abs(b["lambda_"])
+    assert np.abs(r.kf_state[:, 0:3] - o.kf_state[:, 0:3]).max() <= state_atol  # P
+    assert np.abs(r.kf_state[:, 3:6] - o.kf_state[:, 3:6]).max() <= state_atol  # V
+    assert np.abs(r.kf_state[:, 6:10] - o.kf_state[:, 6:10]).max() <= state_atol  # R (quaternion)
+    assert np.abs(r.kf_state[:, 16:22] - o.kf_state[:, 16:22]).max() <= state_atol  # dbg, dba
+    assert np.array_equal(r.kf_state[:, 10:16], w.kf_state[:, 10:16])  # base biases untouched
+    assert np.abs(r.pt_xyz - o.pt_xyz).max() <= state_atol
+    assert np.array_equal(r.obs_outlier, o.obs_outlier)
+    assert np.allclose(r.obs_chi2, o.obs_chi2, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "c1"])
+def test_local_ba_matches_oracle(ctx, oracle, name):
+    w = synth.make_config(name)
+    _compare(ctx.local_ba(w), oracle.local_ba(w), w)
+
+
+def test_local_ba_c3_headline_window(ctx, oracle):
+    w = synth.make_config("c3")
+    r, o = ctx.local_ba(w), oracle.local_ba(w)
+    _compare(r, o, w)
+    assert len(r.trace) == 15
+
+
+def test_extra_fixed_keyframes(ctx, oracle):
+    w = synth.make_config("small", n_fixed_extra=3)
+    r, o = ctx.local_ba(w), oracle.local_ba(w)
+    _compare(r, o, w)
+    fixed = (w.kf_flags & capi.KF_FIXED) != 0
+    assert np.array_equal(r.kf_state[fixed], w.kf_state[fixed])
+
+
+def test_other_seeds_and_ragged_windows(ctx, oracle):
+    for wi in range(1, 4):
+        w = synth.make_config("small", window_index=wi, n_fixed_extra=wi % 2, outlier_frac=0.05 * wi)
+        _compare(ctx.local_ba(w), oracle.local_ba(w), w)
+
+
+def test_resident_solve_is_repeatable(ctx, oracle):
+    w = synth.make_config("small")
+    ctx.upload(w)
+    a = ctx.solve_resident()
+    b = ctx.solve_resident()  # restarts from the uploaded state
+    assert [t["trials"] for t in a.trace] == [t["trials"] for t in b.trace]
+    for x, y in zip(a.trace, b.trace):
+        assert abs(x["chi2_final"] - y["chi2_final"]) <= 1e-9 * abs(y["chi2_final"])
+    _compare(ctx.download().take_trace(b) if hasattr(capi.Result, "take_trace") else _merge(ctx.download(), b),
+             oracle.local_ba(w), w)
+
+
+def _merge(downloaded, solved):
+    downloaded.trace = solved.trace
+    downloaded.status = solved.status
+    downloaded.stage2_ran = solved.stage2_ran
+    downloaded.n_outliers_stage1 = solved.n_outliers_stage1
+    return downloaded
+
+
+def test_stop_flag(ctx, oracle):
+    w = synth.make_config("tiny")
+    r = ctx.local_ba(w, stop_flag=np.ones(1, np.uint8))
+    assert r.status == capi.ABORTED and not r.trace and not r.kf_state.any()
+    r = ctx.local_ba(w, stop_flag=np.zeros(1, np.uint8))
+    assert r.status == 0 and len(r.trace) > 0
+
+
+def test_batch_entry(ctx, oracle):
+    wins = [synth.make_config("tiny", window_index=i) for i in range(3)]
+    rs = ctx.local_ba_batch(wins)
+    for w, r in zip(wins, rs):
+        _compare(r, oracle.local_ba(w), w)
+
+
+def test_invalid_window_is_rejected(ctx, vilba):
+    w = synth.make_config("tiny")
+    w.obs_kf = w.obs_kf.copy()
+    w.obs_kf[0] = 99
+    with pytest.raises(vilba.VilbaError):
+        ctx.local_ba(w)
+
+
+# ---- entry 2 -------------------------------------------------------------------------------------
+def _cmp_preint(got, ref):
+    assert np.allclose(got[:, 0:6], ref[:, 0:6], rtol=0, atol=1e-12)  # dP, dV
+    assert np.allclose(got[:, 6:15], ref[:, 6:15], rtol=0, atol=1e-12)  # dR
+    assert np.allclose(got[:, 15:60], ref[:, 15:60], rtol=1e-10, atol=1e-13)  # bias Jacobians
+    assert np.allclose(got[:, 60:141], ref[:, 60:141], rtol=1e-10, atol=1e-24)  # covariance
+    assert np.allclose(got[:, 141], ref[:, 141], rtol=1e-14)
+
+
+def test_preintegrate_batch_c2(ctx, oracle):
+    b = synth.make_imu_batch(n_pairs=4096, n_samples=40)
+    got = ctx.preintegrate_batch(b.sample_begin, b.gyro, b.acc, b.dt, b.bg, b.ba)
+    ref = oracle.preintegrate_batch(b.sample_begin, b.gyro, b.acc, b.dt, b.bg, b.ba)
+    _cmp_preint(got, ref)
+
+
+def test_preintegrate_ragged_leading_partial(ctx, oracle):
+    b = synth.make_imu_batch(n_pairs=333, seed=77, ragged=True, leading_partial=True)
+    got = ctx.preintegrate_batch(b.sample_begin, b.gyro, b.acc, b.dt, b.bg, b.ba)
+    ref = oracle.preintegrate_batch(b.sample_begin, b.gyro, b.acc, b.dt, b.bg, b.ba)
+    _cmp_preint(got, ref)
+
+
+def test_preintegrate_empty_and_single(ctx, oracle):
+    assert ctx.preintegrate_batch(np.zeros(1, np.int32), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0),
+                                  np.zeros((0, 3)), np.zeros((0, 3))).shape == (0, 142)
+    # a pair with zero samples keeps the reset state (IMUPreintegrator.cpp:39-56)
+    sb = np.array([0, 0, 3], np.int32)
+    g = np.random.default_rng(0).normal(size=(3, 3))
+    a = np.random.default_rng(1).normal(size=(3, 3))
+    got = ctx.preintegrate_batch(sb, g, a, np.full(3, 0.005), np.zeros((2, 3)), np.zeros((2, 3)))
+    ref = oracle.preintegrate_batch(sb, g, a, np.full(3, 0.005), np.zeros((2, 3)), np.zeros((2, 3)))
+    expect0 = np.zeros(142)
+    expect0[6:15] = np.eye(3).reshape(-1)
+    assert np.array_equal(got[0], expect0)
+    _cmp_preint(got, ref)
+
+
+def test_preintegrate_closed_forms_on_device(ctx):
+    S, h = 40, 0.005
+    a = np.array([0.3, -1.2, 9.0])
+    sb = np.array([0, S], np.int32)
+    out = ctx.preintegrate_batch(sb, np.zeros((S, 3)), np.tile(a, (S, 1)), np.full(S, h), np.zeros((1, 3)), np.zeros((1, 3)))[0]
+    T = S * h
+    assert np.allclose(out[3:6], a * T, rtol=1e-13) and np.allclose(out[0:3], 0.5 * a * T * T, rtol=1e-13)
+    assert np.allclose(out[6:15].reshape(3, 3), np.eye(3), atol=1e-15)
