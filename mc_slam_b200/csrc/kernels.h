@@ -9,7 +9,7 @@ namespace vilba {
 
 constexpr int kPreintThreads = 256;
 constexpr int kPointThreads = 256;  // 8 warps per CTA, one warp per map point
-constexpr int kCholThreads = 1024;
+constexpr int kCholThreads = 512;
 constexpr int kCholNB = 16;
 constexpr int kMaxKF = 256;          // key-frames per window supported by the shared-memory stage
 
@@ -66,6 +66,7 @@ struct DevWindow {
     double* bl;   // P * 3
     double* W;    // E * 18  H_pl block of the edge, 6x3 rows [P,Phi]
     double* S;    // n * n   reduced camera system (upper triangle used)
+    double* Lfac; // n * n   Cholesky factor of S (same addressing as S)
     double* bs;   // n
     double* x;    // n       pose increment
     LmState* lm;
@@ -98,7 +99,8 @@ cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow& w);
 cudaError_t launch_update_eval(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, bool apply);
 cudaError_t launch_linearize(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
 cudaError_t launch_schur(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
-cudaError_t launch_chol_solve(cudaStream_t s, const DevWindow& w);
+cudaError_t launch_chol_solve(cudaStream_t s, const DevWindow& w);           // v1 single-CTA kernel (kept for A/B)
+cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow& w, int cluster_size);
 // LM bookkeeping kernels (single CTA)
 cudaError_t launch_lm_stage_begin(cudaStream_t s, const DevWindow& w);   // current_chi = chi_acc
 cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow& w, int iteration);

@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(kPointThreads) schur_points_kernel(DevWindow w
 // L(i,j), i >= j, lives at S[j*n + i].  The right-hand side rides along as an extra row, so the
 // forward substitution is a by-product of the panel solves; a single warp then back-substitutes.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(DevWindow w) {
+__global__ void __launch_bounds__(1024) chol_solve_kernel(DevWindow w) {
     constexpr int NB = kCholNB;
     extern __shared__ double smem[];
     const int n = w.n;
@@ -982,7 +982,7 @@ cudaError_t launch_chol_solve(cudaStream_t s, const DevWindow& w) {
         if (e != cudaSuccess) return e;
         configured = sm;
     }
-    chol_solve_kernel<<<1, kCholThreads, sm, s>>>(w);
+    chol_solve_kernel<<<1, 1024, sm, s>>>(w);
     return cudaGetLastError();
 }
 

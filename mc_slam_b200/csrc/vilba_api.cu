@@ -7,6 +7,7 @@
 // CUDA device vilba_create() returns NULL.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,7 +65,7 @@ struct Layout {
     // input section (one H2D copy)
     size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, input_end;
     // work section
-    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, S, bs, x, lm, n_culled,
+    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, S, Lfac, bs, x, lm, n_culled,
         outlier, total;
 };
 
@@ -97,6 +98,7 @@ Layout make_layout(int K, int NI, int P, int E, int n) {
     L.bl = take(sizeof(double) * 3 * (size_t)P);
     L.W = take(sizeof(double) * 18 * (size_t)E);
     L.S = take(sizeof(double) * (size_t)n * n);
+    L.Lfac = take(sizeof(double) * (size_t)n * n);
     L.bs = take(sizeof(double) * (size_t)n);
     L.x = take(sizeof(double) * (size_t)n);
     L.lm = take(sizeof(LmState));
@@ -126,6 +128,7 @@ struct vilba_ctx {
     // stats
     vilba_stats stats;
     bool profiling = false;
+    int chol_cluster = 8;  // CTAs in the Cholesky cluster (0 = v1 single-CTA kernel); env VILBA_CHOL_CLUSTER
     std::vector<cudaEvent_t> prof_events;  // pairs, drained at sync points
     std::vector<int> prof_kind;
     size_t prof_used = 0;
@@ -265,6 +268,7 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     dw.bl = reinterpret_cast<double*>(d + L.bl);
     dw.W = reinterpret_cast<double*>(d + L.W);
     dw.S = reinterpret_cast<double*>(d + L.S);
+    dw.Lfac = reinterpret_cast<double*>(d + L.Lfac);
     dw.bs = reinterpret_cast<double*>(d + L.bs);
     dw.x = reinterpret_cast<double*>(d + L.x);
     dw.lm = reinterpret_cast<LmState*>(d + L.lm);
@@ -359,7 +363,10 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, int n_active, vilba_res
             CK(launch_schur(s, dw, ctx->cfg), "schur");
             prof_end(ctx);
             prof_begin(ctx, 2);
-            CK(launch_chol_solve(s, dw), "chol");
+            if (ctx->chol_cluster > 0)
+                CK(launch_chol_cluster(s, dw, ctx->chol_cluster), "chol_cluster");
+            else
+                CK(launch_chol_solve(s, dw), "chol");
             prof_end(ctx);
             CK(launch_update_eval(s, dw, ctx->cfg, true), "update_eval");
             if (stop_requested(stop_flag)) {
@@ -510,6 +517,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::atoi(e);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
         std::fprintf(stderr, "vilba_create: %s\n", cudaGetErrorString(cudaGetLastError()));
