@@ -4,16 +4,22 @@
 // matrix).  A non-positive pivot raises LmState::chol_fail => the LM controller rejects the trial,
 // like the `ok2 == false` path of optimization_algorithm_levenberg.cpp:126-127.
 //
-// Latency-oriented design for one thread-block cluster (1..16 CTAs on neighbouring SMs):
+// The factorisation is latency-bound (n sequential pivots), so everything is organised around the
+// serial chain, for one thread-block cluster (1..16 CTAs on neighbouring SMs):
 //   * the matrix stays in global memory (L2-resident, <= 17.6 MB); the upper triangle of the row-major
 //     S is addressed as the lower triangle of a column-major matrix, L(i,j) at S[j*n+i];
 //   * right-looking, NB=16 columns per step.  EVERY CTA redundantly factors the 16x16 diagonal block
-//     (one warp, rows in registers, broadcasts by shuffle) and solves the whole panel (one row per
-//     thread), so the panel never has to be exchanged between CTAs;
-//   * the rank-16 trailing update is split over the cluster in 4x4 register tiles whose old values are
+//     and solves the whole panel (one row per thread), so nothing but the trailing matrix is exchanged;
+//   * the diagonal block is factored by one warp in square-root-free LDL^T form with 4x4 micro-blocks:
+//     the 4x4 pivot block is broadcast through shared memory once and factored redundantly by every
+//     lane (4 reciprocals on the chain, no per-column communication); square roots are taken once per
+//     block, off the chain;
+//   * the rank-16 trailing update is split over the cluster in 4x4 register tiles (rows/columns strided
+//     so that panel reads are bank-conflict free and global accesses coalesce); old values are
 //     prefetched from L2 before the panel is ready; ONE hardware cluster barrier per step publishes them;
-//   * the right-hand side rides along as an extra matrix row, so the forward substitution costs
-//     nothing; CTA 0 back-substitutes with per-block warp solves.
+//   * the right-hand side rides along as an extra matrix row, so the forward substitution is free;
+//     CTA 0 back-substitutes: per block one warp holds L11^T in registers (one multiply + one shuffle
+//     + one fma on the chain per unknown), the other threads apply the block row with prefetched data.
 #include <cooperative_groups.h>
 
 #include "kernels.h"
@@ -25,31 +31,78 @@ namespace vilba {
 
 namespace {
 
-constexpr int NB = kCholNB;       // 16
-constexpr int LDP = NB + 1;       // padded shared-memory row stride (bank-conflict free for column walks)
+constexpr int NB = kCholNB;   // 16
+constexpr int LDP = NB + 1;   // padded shared-memory row stride of the panel (conflict-free column walks)
 
-// Cholesky of a jb x jb block held one row per lane (row r in lane r, entries a[0..r]).
-// Returns false if a pivot is not positive.
-__device__ __forceinline__ bool warp_potrf16(double (&a)[NB], int lane, int jb, double& my_inv) {
+// ~1 ulp reciprocal: MUFU seed + two Newton steps (shorter dependent chain than an IEEE division)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
+// LDL^T of a 16x16 block held one row per lane (lane r: a[c] = A(r,c) for c <= r; rows/cols beyond
+// the real size are identity-padded by the caller).  On return lane r holds the unit-lower l(r,c) in
+// a[c], c < r, and d_r in a[r].  `sm` is 16 + 64 doubles of warp-private shared memory.
+__device__ __forceinline__ bool warp_ldlt16_mb4(double (&a)[NB], int lane, double* sm) {
+    double* Bc = sm;       // 4 x 4  pivot block
+    double* Lb = sm + 16;  // 16 x 4 scaled rows l(r, j..j+3)
     bool ok = true;
-    my_inv = 0.0;
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        if (j < jb) {
-            const double ajj = __shfl_sync(0xffffffffu, a[j], j);
-            if (!(ajj > 0.0)) ok = false;
-            const double inv = 1.0 / sqrt(ajj);
-            if (lane == j) my_inv = inv;  // 1 / L(j,j)
-            if (lane == j)
-                a[j] = ajj * inv;
-            else if (lane > j)
-                a[j] *= inv;
+    for (int s = 0; s < 4; ++s) {
+        const int j = 4 * s;
+        if (lane >= j && lane < j + 4) {
+            double* p = Bc + 4 * (lane - j);
+            p[0] = a[j], p[1] = a[j + 1], p[2] = a[j + 2], p[3] = a[j + 3];
+        }
+        __syncwarp();
+        const double b00 = Bc[0], b10 = Bc[4], b20 = Bc[8], b30 = Bc[12];
+        double b11 = Bc[5], b21 = Bc[9], b31 = Bc[13], b22 = Bc[10], b32 = Bc[14], b33 = Bc[15];
+        // 4x4 LDL^T, redundantly in every lane
+        const double d0 = b00, r0 = fast_rcp(d0);
+        const double l10 = b10 * r0, l20 = b20 * r0, l30 = b30 * r0;
+        b11 -= l10 * b10, b21 -= l20 * b10, b31 -= l30 * b10;
+        b22 -= l20 * b20, b32 -= l30 * b20, b33 -= l30 * b30;
+        const double d1 = b11, r1 = fast_rcp(d1);
+        const double l21 = b21 * r1, l31 = b31 * r1;
+        b22 -= l21 * b21, b32 -= l31 * b21, b33 -= l31 * b31;
+        const double d2 = b22, r2 = fast_rcp(d2);
+        const double l32 = b32 * r2;
+        b33 -= l32 * b32;
+        const double d3 = b33, r3 = fast_rcp(d3);
+        if (!(d0 > 0.0) || !(d1 > 0.0) || !(d2 > 0.0) || !(d3 > 0.0)) ok = false;
+        // rows below the pivot block: u = A(r, j..j+3) Lb^-T (unscaled), l = u D^-1
+        double u0 = a[j], u1 = a[j + 1], u2 = a[j + 2], u3 = a[j + 3];
+        u1 -= u0 * l10;
+        u2 -= u0 * l20 + u1 * l21;
+        u3 -= u0 * l30 + u1 * l31 + u2 * l32;
+        const double q0 = u0 * r0, q1 = u1 * r1, q2 = u2 * r2, q3 = u3 * r3;
+        if (lane >= j + 4) {
+            a[j] = q0, a[j + 1] = q1, a[j + 2] = q2, a[j + 3] = q3;
+            if (lane < NB) {
+                double* p = Lb + 4 * lane;
+                p[0] = q0, p[1] = q1, p[2] = q2, p[3] = q3;
+            }
+        } else if (lane >= j) {  // rows of the pivot block itself
+            const int i = lane - j;
+            a[j] = (i == 0) ? d0 : (i == 1) ? l10 : (i == 2) ? l20 : l30;
+            a[j + 1] = (i == 1) ? d1 : (i == 2) ? l21 : (i == 3) ? l31 : 0.0;
+            a[j + 2] = (i == 2) ? d2 : (i == 3) ? l32 : 0.0;
+            a[j + 3] = (i == 3) ? d3 : 0.0;
+        }
+        if (s < 3) {
+            __syncwarp();
+            // trailing part of the block: A(r,c) -= sum_k u(r,k) l(c,k), c = j+4 .. r
 #pragma unroll
-            for (int c = j + 1; c < NB; ++c) {
-                const double lcj = __shfl_sync(0xffffffffu, a[j], c);  // L(c,j)
-                if (c < jb && lane >= c) a[c] -= a[j] * lcj;
+            for (int c = j + 4; c < NB; ++c) {
+                const double* p = Lb + 4 * c;
+                if (lane >= c) a[c] -= u0 * p[0] + u1 * p[1] + u2 * p[2] + u3 * p[3];
             }
         }
+        __syncwarp();
     }
     return ok;
 }
@@ -62,56 +115,98 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(DevWindow w)
     const int csize = (int)cluster.num_blocks();
     extern __shared__ double smem[];
     const int n = w.n;
-    double* D = smem;                         // NB x LDP   factored diagonal block L11
-    double* Pn = smem + NB * LDP;             // (n + 1) x LDP  panel L21 (+ rhs row)
-    double* xs = Pn + (size_t)(n + 1) * LDP;  // n  solution during back substitution
-    double* Dinv = xs + n;                    // NB  reciprocals of the diagonal of L11
+    double* Dt = smem;                        // NB x NB   unit-lower L11, transposed: Dt[k*NB + c] = l(c,k)
+    double* Pn = Dt + NB * NB;                // (n + 8) x LDP  panel X = A21 L11^-T D^-1/2 (+ rhs row + zero pad)
+    double* xs = Pn + (size_t)(n + 8) * LDP;  // n   solution during back substitution
+    double* Dsq = xs + n;                     // NB  sqrt(d)
+    double* Dis = Dsq + NB;                   // NB  1/sqrt(d)
+    double* Wsm = Dis + NB;                   // 80  warp-private scratch of the diagonal factorisation
     double* A = w.S;       // working matrix: column block k is only READ in step k, the trailing part is updated
     double* Lf = w.Lfac;   // factor output (same addressing); written by CTA 0, never read inside the loop
     double* y = w.bs;      // rhs row, updated like a matrix row
     double* yf = w.x;      // forward-substituted rhs (L^-1 b), later overwritten by the solution
+    double* rdiag = w.cdinv;  // 1 / L(j,j), written by CTA 0 for the back substitution
     __shared__ int s_fail;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31;
     if (tid == 0) s_fail = 0;
     __syncthreads();
+#ifdef VILBA_CHOL_TIMING
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tq = clock64();
+#define TPH(i) { long long tn_ = clock64(); tph[i] += tn_ - tq; tq = tn_; }
+#else
+#define TPH(i)
+#endif
 
+    // warp 0 is the dedicated factor warp; warps 1.. are the panel/tile workers
+    const bool is_factor_warp = tid < 32;
+    const int wt = tid - 32, nwt = nt - 32;  // worker thread index / count
     for (int j0 = 0; j0 < n; j0 += NB) {
         const int jb = min(NB, n - j0);
         const int rows_below = n - j0 - jb;
-        const int m_rows = rows_below + 1;  // + the rhs row
-        // ---- (1) loads: diagonal block rows into warp 0's registers, panel rows into registers ----
-        double drow[NB];
-        if (tid < 32) {
-#pragma unroll
-            for (int c = 0; c < NB; ++c)
-                drow[c] = (lane < jb && c <= lane && c < jb) ? A[(size_t)(j0 + c) * n + j0 + lane] : 0.0;
-        }
-        // first panel row of this thread (prefetched before the diagonal block is ready)
+        const int m_rows = rows_below + 1;       // + the rhs row
+        const int trp = (m_rows + 3) >> 2;       // 4-row groups of the panel
+        // lower-triangular 4x4 tiles over (m_rows) x (rows_below): tile (ti,tj), tj <= ti
+        const int ntiles = trp * (trp + 1) / 2;
+        const int gthreads = csize * nwt;
+        const int t_first = crank * nwt + wt;
         double xr0[NB];
-        {
-            const int rr = tid;
-            const bool is_rhs = (rr == rows_below);
-            const int gi = j0 + jb + rr;
+        double old[4][4];
+        int ti0 = 0, tj0 = 0;
+        if (is_factor_warp) {
+            // ---- factor warp: (1) load the diagonal block (identity padded), (3) factor, publish ----
+            double drow[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                double v = (c == lane) ? 1.0 : 0.0;
+                if (lane < jb && c <= lane) v = A[(size_t)(j0 + c) * n + j0 + lane];
+                drow[c] = v;
+            }
+            TPH(0)
+            const bool ok = warp_ldlt16_mb4(drow, lane, Wsm);
+            if (!ok && lane == 0) s_fail = 1;
+            double dr = 1.0;
 #pragma unroll
             for (int c = 0; c < NB; ++c)
-                xr0[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * n + gi]) : 0.0;
-        }
-        // ---- (2) prefetch the old values of this thread's first trailing tile ----
-        const int tr = (m_rows + 3) >> 2, tc = (rows_below + 3) >> 2;
-        const int ntiles = tr * tc;
-        const int gthreads = csize * nt;
-        const int t_first = crank * nt + tid;
-        double old[4][4];
-        {
-            const int t = t_first;
-            const int tj = t / tr, ti = t - tj * tr;
-            if (t < ntiles && ti >= tj) {
+                if (c == lane) dr = drow[c];
+            const double sq = sqrt(dr), isq = 1.0 / sq;
+            if (lane < NB) {
+                Dsq[lane] = sq;
+                Dis[lane] = isq;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) Dt[c * NB + lane] = (c < lane) ? drow[c] : 0.0;  // l(lane,c)
+            }
+            __syncwarp();
+            if (crank == 0 && lane < jb) {  // Cholesky factor block: L(r,c) = l(r,c) sqrt(d_c), L(r,r) = sqrt(d_r)
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c <= lane) Lf[(size_t)(j0 + c) * n + j0 + lane] = (c == lane) ? sq : drow[c] * Dsq[c];
+                rdiag[j0 + lane] = isq;
+            }
+            TPH(1)
+        } else {
+            // ---- workers: (1) first panel row of the thread, (2) old values of its first tile ----
+            {
+                const int rr = wt;
+                const bool is_rhs = (rr == rows_below);
+                const int gi = j0 + jb + rr;
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    xr0[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * n + gi]) : 0.0;
+            }
+            if (t_first < ntiles) {
+                // triangular decode: t = ti (ti + 1) / 2 + tj
+                int ti = (int)((sqrtf(8.0f * (float)t_first + 1.0f) - 1.0f) * 0.5f);
+                while (ti * (ti + 1) / 2 > t_first) --ti;
+                while ((ti + 1) * (ti + 2) / 2 <= t_first) ++ti;
+                ti0 = ti;
+                tj0 = t_first - ti * (ti + 1) / 2;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const int r = 4 * ti + a, c = 4 * tj + b;
+                        const int r = 4 * ti0 + a, c = 4 * tj0 + b;
                         double v = 0.0;
                         if (r < m_rows && c < rows_below && c <= r)
                             v = (r == rows_below) ? y[j0 + jb + c] : A[(size_t)(j0 + jb + c) * n + (j0 + jb + r)];
@@ -119,155 +214,174 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(DevWindow w)
                     }
             }
         }
-        // ---- (3) factor the diagonal block (warp 0), publish to shared ----
-        if (tid < 32) {
-            double my_inv;
-            const bool ok = warp_potrf16(drow, lane, jb, my_inv);
-            if (!ok && lane == 0) s_fail = 1;
-            if (lane < NB) Dinv[lane] = my_inv;
-            if (lane < NB) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c) D[lane * LDP + c] = drow[c];
-            }
-            if (crank == 0 && lane < jb) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c <= lane && c < jb) Lf[(size_t)(j0 + c) * n + j0 + lane] = drow[c];
-            }
-        }
         __syncthreads();
-        // ---- (4) panel: X L11^T = A21, one row per thread (every CTA solves all rows) ----
-        for (int rr = tid; rr < m_rows; rr += nt) {
-            double xr[NB];
-            const bool is_rhs = (rr == rows_below);
-            const int gi = j0 + jb + rr;
-            if (rr == tid) {
+        TPH(2)
+        // ---- (4) panel: Z L11^T = A21 with unit-lower L11 (right-looking inside the row: one fma on
+        //      the serial chain per column), then X = Z D^-1/2.  Every CTA solves all rows.  Row r is
+        //      stored at position (r & 3) * trp + (r >> 2) so that the 4 rows of a tile are read
+        //      bank-conflict free; the rows of the last (partial) group are zero. ----
+        if (!is_factor_warp) {
+            for (int rr = wt; rr < 4 * trp; rr += nwt) {
+                double xr[NB];
+                const bool is_rhs = (rr == rows_below);
+                const int gi = j0 + jb + rr;
+                if (rr == wt) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) xr[c] = xr0[c];
-            } else {
+                    for (int c = 0; c < NB; ++c) xr[c] = xr0[c];
+                } else {
 #pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    xr[c] = (c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * n + gi]) : 0.0;
-            }
+                    for (int c = 0; c < NB; ++c)
+                        xr[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * n + gi]) : 0.0;
+                }
 #pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                if (c < jb) {
-                    double s = xr[c];
+                for (int k = 0; k < NB - 1; ++k) {
 #pragma unroll
-                    for (int k = 0; k < c; ++k) s -= xr[k] * D[c * LDP + k];
-                    xr[c] = s * Dinv[c];
+                    for (int c = k + 1; c < NB; ++c) xr[c] -= xr[k] * Dt[k * NB + c];  // l(c,k)
+                }
+                double* prow = Pn + (size_t)((rr & 3) * trp + (rr >> 2)) * LDP;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    xr[c] *= Dis[c];
+                    prow[c] = xr[c];
+                }
+                if (crank == 0 && rr < m_rows) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c)
+                        if (c < jb) {
+                            if (is_rhs)
+                                yf[j0 + c] = xr[c];
+                            else
+                                Lf[(size_t)(j0 + c) * n + gi] = xr[c];
+                        }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < NB; ++c) Pn[(size_t)rr * LDP + c] = xr[c];
-            if (crank == 0) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < jb) {
-                        if (is_rhs)
-                            yf[j0 + c] = xr[c];
-                        else
-                            Lf[(size_t)(j0 + c) * n + gi] = xr[c];
-                    }
-            }
         }
+        TPH(3)
         __syncthreads();
-        // ---- (5) trailing update A22 -= P P^T (and rhs -= P_rhs P^T), tiles split over the cluster ----
-        for (int t = t_first; t < ntiles; t += gthreads) {
-            const int tj = t / tr, ti = t - tj * tr;
-            if (ti < tj) continue;
-            const int r0 = 4 * ti, c0 = 4 * tj;
-            double acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-            const double* pr = Pn + (size_t)min(r0, m_rows - 1) * LDP;
-            const double* pc = Pn + (size_t)min(c0, m_rows - 1) * LDP;
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                double vr[4], vc[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    vr[a] = (r0 + a < m_rows) ? pr[a * LDP + k] : 0.0;
-                    vc[a] = (c0 + a < rows_below) ? pc[a * LDP + k] : 0.0;
+        TPH(4)
+        // ---- (5) trailing update A22 -= X X^T (and rhs -= x_rhs X^T), lower tiles split over the cluster ----
+        if (!is_factor_warp) {
+            for (int t = t_first; t < ntiles; t += gthreads) {
+                int ti, tj;
+                if (t == t_first) {
+                    ti = ti0, tj = tj0;
+                } else {
+                    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                    while (ti * (ti + 1) / 2 > t) --ti;
+                    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+                    tj = t - ti * (ti + 1) / 2;
                 }
+                double acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] += vr[a] * vc[b];
-            }
-            const bool pre = (t == t_first);
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+                const double* pr = Pn + (size_t)ti * LDP;
+                const double* pc = Pn + (size_t)tj * LDP;
+                const int sr = trp * LDP;
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int r = r0 + a, c = c0 + b;
-                    if (r >= m_rows || c >= rows_below || c > r) continue;
-                    double* p = (r == rows_below) ? &y[j0 + jb + c] : &A[(size_t)(j0 + jb + c) * n + (j0 + jb + r)];
-                    const double o = pre ? old[a][b] : *p;
-                    *p = o - acc[a][b];
+                for (int k = 0; k < NB; ++k) {
+                    const double vr0 = pr[k], vr1 = pr[sr + k], vr2 = pr[2 * sr + k], vr3 = pr[3 * sr + k];
+                    const double vc0 = pc[k], vc1 = pc[sr + k], vc2 = pc[2 * sr + k], vc3 = pc[3 * sr + k];
+                    acc[0][0] += vr0 * vc0, acc[0][1] += vr0 * vc1, acc[0][2] += vr0 * vc2, acc[0][3] += vr0 * vc3;
+                    acc[1][0] += vr1 * vc0, acc[1][1] += vr1 * vc1, acc[1][2] += vr1 * vc2, acc[1][3] += vr1 * vc3;
+                    acc[2][0] += vr2 * vc0, acc[2][1] += vr2 * vc1, acc[2][2] += vr2 * vc2, acc[2][3] += vr2 * vc3;
+                    acc[3][0] += vr3 * vc0, acc[3][1] += vr3 * vc1, acc[3][2] += vr3 * vc2, acc[3][3] += vr3 * vc3;
                 }
+                const bool pre = (t == t_first);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = 4 * ti + a, c = 4 * tj + b;
+                        if (r >= m_rows || c >= rows_below || c > r) continue;
+                        double* p =
+                            (r == rows_below) ? &y[j0 + jb + c] : &A[(size_t)(j0 + jb + c) * n + (j0 + jb + r)];
+                        const double o = pre ? old[a][b] : *p;
+                        *p = o - acc[a][b];
+                    }
+            }
         }
+        TPH(5)
         // ---- (6) publish the updated trailing matrix to the whole cluster ----
         if (csize > 1)
             cluster.sync();
         else
             __syncthreads();
+        TPH(6)
     }
 
     // ---- back substitution L^T x = y on CTA 0 ----
     if (crank != 0) return;
-    __syncthreads();  // CTA 0's own writes to yf / Lf are ordered by the block barrier
+    __syncthreads();  // CTA 0's own writes to yf / Lf / rdiag are ordered by the block barrier
     for (int i = tid; i < n; i += nt) xs[i] = yf[i];
-    __syncthreads();
     const int nblk = (n + NB - 1) / NB;
+    double lcol[NB];   // warp 0: lane c holds column c of the diagonal block, L(j0+j, j0+c), j >= c
+    double lrow[NB];   // all threads: thread c holds L(j0+t, c), t = 0..15, for its column c < j0
+    double rd = 0.0;
+    auto prefetch = [&](int kb) {
+        const int j0 = kb * NB;
+        const int jb = min(NB, n - j0);
+        if (tid < 32) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                lcol[j] = (lane < jb && j < jb && j >= lane) ? Lf[(size_t)(j0 + lane) * n + j0 + j] : 0.0;
+            rd = (lane < jb) ? rdiag[j0 + lane] : 0.0;
+        }
+        if (tid < j0) {
+            const double* col = Lf + (size_t)tid * n + j0;
+#pragma unroll
+            for (int t = 0; t < NB; ++t) lrow[t] = (t < jb) ? col[t] : 0.0;
+        }
+    };
+    prefetch(nblk - 1);
+    __syncthreads();
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int j0 = kb * NB;
         const int jb = min(NB, n - j0);
-        // prefetch this thread's slice of block row kb of L for the update below: L(j0+t, c), c < j0
-        // (one column c per thread)
         if (tid < 32) {
-            // solve L11^T x_b = y_b : row r of L11 in lane r
-            double lrow[NB];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) lrow[c] = (lane < jb && c <= lane) ? Lf[(size_t)(j0 + c) * n + j0 + lane] : 0.0;
-            double xv = (lane < jb) ? xs[j0 + lane] : 0.0;
+            double yv = (lane < jb) ? xs[j0 + lane] : 0.0;
 #pragma unroll
             for (int j = NB - 1; j >= 0; --j) {
-                if (j < jb) {
-                    // x_j = y_j / L(j,j); then y_c -= L(j,c) x_j for c < j   (L(j,c) lives in lane j, entry c)
-                    const double ljj = __shfl_sync(0xffffffffu, lrow[j], j);
-                    const double xj = __shfl_sync(0xffffffffu, xv, j) / ljj;
-                    if (lane == j) xv = xj;
-                    // lane c needs L(j,c): held by lane j at index c -> dynamic index; use a shuffle per c
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) {
-                        const double ljc = __shfl_sync(0xffffffffu, lrow[c], j);
-                        if (lane == c && c < j) xv -= ljc * xj;
-                    }
-                }
+                // x_j = y_j / L(j,j) in lane j, broadcast, then y_c -= L(j,c) x_j for c < j
+                const double xj = __shfl_sync(0xffffffffu, yv * rd, j);
+                if (lane == j) yv = xj;
+                if (lane < j) yv -= lcol[j] * xj;
             }
-            if (lane < jb) xs[j0 + lane] = xv;
+            if (lane < jb) xs[j0 + lane] = yv;
         }
         __syncthreads();
-        // y_c -= sum_t L(j0+t, c) x(j0+t) for all c < j0
-        for (int c = tid; c < j0; c += nt) {
+        // y_c -= sum_t L(j0+t, c) x(j0+t) for c < j0, with the block row prefetched one step ahead
+        double s = 0.0;
+        if (tid < j0) {
+#pragma unroll
+            for (int t = 0; t < NB; ++t) s += lrow[t] * xs[j0 + t];
+        }
+        for (int c = tid + nt; c < j0; c += nt) {  // n > blockDim: remaining columns without prefetch
             const double* col = Lf + (size_t)c * n + j0;
-            double s = 0.0;
+            double s2 = 0.0;
 #pragma unroll
             for (int t = 0; t < NB; ++t)
-                if (t < jb) s += col[t] * xs[j0 + t];
-            xs[c] -= s;
+                if (t < jb) s2 += col[t] * xs[j0 + t];
+            xs[c] -= s2;
         }
+        if (kb > 0) prefetch(kb - 1);
+        if (tid < j0) xs[tid] -= s;
         __syncthreads();
     }
     for (int i = tid; i < n; i += nt) w.x[i] = xs[i];
     if (tid == 0) w.lm->chol_fail = s_fail;
+#ifdef VILBA_CHOL_TIMING
+    TPH(7)
+    if (tid == 0 && w.dbg) {
+        for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)&w.dbg[i], (unsigned long long)tph[i]);
+        atomicAdd((unsigned long long*)&w.dbg[8], 1ull);
+    }
+#endif
 }
 
 static size_t chol_cluster_smem(int n) {
-    return sizeof(double) * ((size_t)NB * LDP + (size_t)(n + 1) * LDP + (size_t)n + NB);
+    return sizeof(double) * ((size_t)NB * NB + (size_t)(n + 8) * LDP + (size_t)n + 2 * NB + 80);
 }
 
 cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow& w, int cluster_size) {

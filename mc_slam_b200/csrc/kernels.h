@@ -67,9 +67,23 @@ struct DevWindow {
     double* W;    // E * 18  H_pl block of the edge, 6x3 rows [P,Phi]
     double* S;    // n * n   reduced camera system (upper triangle used)
     double* Lfac; // n * n   Cholesky factor of S (same addressing as S)
+    double* cdinv; // n      1 / L(j,j)
     double* bs;   // n
     double* x;    // n       pose increment
+    // v2 (atomic-free) accumulation
+    double* lin_partial;     // lin_ctas * n_free * 27   per-CTA partial pose blocks of the mono edges
+    double* imu_slot;        // NI * 930                 30x30 block + 30 rhs of every IMU edge pair
+    const int* blk_edge_i;   // n_free: IMU edge in which the block is key-frame i, or -1
+    const int* blk_edge_j;   // n_free: IMU edge in which the block is key-frame j, or -1
+    const int* edge_pt;      // E: map point of every mono edge
+    int n_pairs;             // n_free (n_free + 1) / 2 key-frame block pairs (a <= b)
+    const int* pair_a;       // n_pairs
+    const int* pair_b;       // n_pairs
+    const int* pair_begin;   // n_pairs + 1
+    const int* pair_ea;      // (edge of block a, edge of block b) sharing a map point
+    const int* pair_eb;
     LmState* lm;
+    long long* dbg;  // optional debug counters (16 x int64), may be null
     // calibration (g2otypes.h:686-705)
     double fx, fy, cx, cy;
     double Rcb[9];  // Rbc^T
@@ -99,6 +113,8 @@ cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow& w);
 cudaError_t launch_update_eval(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, bool apply);
 cudaError_t launch_linearize(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
 cudaError_t launch_schur(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
+cudaError_t launch_linearize_v2(cudaStream_t s, const DevWindow& w, int point_ctas);
+cudaError_t launch_schur_gather(cudaStream_t s, const DevWindow& w);
 cudaError_t launch_chol_solve(cudaStream_t s, const DevWindow& w);           // v1 single-CTA kernel (kept for A/B)
 cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow& w, int cluster_size);
 // LM bookkeeping kernels (single CTA)

@@ -1,0 +1,436 @@
+// lba_v2.cu -- atomic-free, run-to-run deterministic versions of the accumulation kernels.
+//
+//   linearize_v2 : same arithmetic as linearize_mono/imu (EdgeNavStatePVRPointXYZ / EdgeNavStatePVR /
+//                  EdgeNavStateBias linearizeOplus + constructQuadraticForm, src/IMU/g2otypes.cpp:587-699,
+//                  724-734,738-788; g2o/core/base_binary_edge.hpp:55-120; base_multi_edge.hpp:171-222), but the
+//                  pose-block contributions of the mono edges are summed in WARP-PRIVATE shared-memory
+//                  accumulators (the edges of one point hit distinct key-frames, so a warp never collides
+//                  with itself), reduced per CTA in a fixed order and written as one partial per CTA;
+//                  every IMU edge pair writes its own 30x30 slot.  IMU CTAs run in the same launch.
+//   assemble_hpp : H_pp / b_p = fixed-order sum of the CTA partials and the IMU slots
+//                  (BlockSolver::buildSystem's flush, g2o/core/block_solver.hpp:547-557).
+//   schur_gather : S(a,b) = H_pp(a,b) + lambda I - sum_l W_a,l D_l^-1 W_b,l^T as a GATHER over precomputed
+//                  (edge_a, edge_b) lists per key-frame block pair, one CTA per block pair, register
+//                  accumulation, fixed reduction tree -- replaces 6.5 M FP64 atomics per LM trial
+//                  (landmark loop of BlockSolver::solve, block_solver.hpp:381-439).
+#include "lba_common.cuh"
+
+namespace vilba {
+
+constexpr int kAccStride = 27;  // 21 upper entries of the 6x6 [P,Phi] block + 6 rhs entries
+
+size_t linearize_v2_smem_bytes(int K, int n_free, int warps) {
+    return kf_smem_bytes(K) + sizeof(double) * (size_t)warps * n_free * kAccStride + 16;
+}
+
+__global__ void __launch_bounds__(kPointThreads) linearize_v2_kernel(DevWindow w, int point_ctas) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cur = w.lm->cur;
+
+    if ((int)blockIdx.x >= point_ctas) {
+        // ======================= IMU edge pair (warp 0 of the CTA) =======================
+        if (warp != 0) return;
+        double* J = smem;            // 9 x 24: PVR_i (9) | Bias_i (6) | PVR_j (9)
+        double* Om = J + 216;        // 81
+        double* TJ = Om + 81;        // 9 x 24  (rho1 Omega) J
+        double* ev = TJ + 216;       // 9
+        double* Oe = ev + 9;         // 9   Omega e
+        double* misc = Oe + 9;       // [0] rho1
+        const int e = blockIdx.x - point_ctas;
+        const int ki = w.imu_i[e], kj = w.imu_j[e];
+        const double* si = w.kf_state[cur] + 22 * (size_t)ki;
+        const double* sj = w.kf_state[cur] + 22 * (size_t)kj;
+        const double* M = w.imu_preint + 142 * (size_t)e;
+        for (int i = lane; i < 81; i += 32) Om[i] = w.imu_info[81 * (size_t)e + i];
+        for (int i = lane; i < 216; i += 32) J[i] = 0.0;
+        __syncwarp();
+        if (lane == 0) {
+            V3 rP, rV, rPhi;
+            pvr_error(w, si, sj, M, rP, rV, rPhi);
+            ev[0] = rP.x, ev[1] = rP.y, ev[2] = rP.z, ev[3] = rV.x, ev[4] = rV.y, ev[5] = rV.z;
+            ev[6] = rPhi.x, ev[7] = rPhi.y, ev[8] = rPhi.z;
+            double rho0, rho1;
+            huber(quad9(Om, ev), w.huber_pvr, rho0, rho1);
+            misc[0] = rho1;
+            for (int r = 0; r < 9; ++r) {
+                double t = 0.0;
+                for (int c = 0; c < 9; ++c) t += Om[9 * r + c] * ev[c];
+                Oe[r] = t;
+            }
+            const V3 Pi = ld3(si), Vi = ld3(si + 3), Pj = ld3(sj), Vj = ld3(sj + 3);
+            const M3 Ri = q_to_matrix(Q4{si[6], si[7], si[8], si[9]});
+            const M3 Rj = q_to_matrix(Q4{sj[6], sj[7], sj[8], sj[9]});
+            const V3 dbg = ld3(si + 16);
+            const V3 g = ld3(w.g);
+            const double T = M[VILBA_PI_DT], T2 = T * T;
+            const M3 RiT = transpose(Ri);
+            const M3 JrInv = jacobian_r_inv(rPhi);
+            const M3 JRg = ldm3(M + VILBA_PI_JRG);
+            auto put = [&](int r0, int c0, const M3& B) {
+                J[(r0 + 0) * 24 + c0 + 0] = B.a00, J[(r0 + 0) * 24 + c0 + 1] = B.a01, J[(r0 + 0) * 24 + c0 + 2] = B.a02;
+                J[(r0 + 1) * 24 + c0 + 0] = B.a10, J[(r0 + 1) * 24 + c0 + 1] = B.a11, J[(r0 + 1) * 24 + c0 + 2] = B.a12;
+                J[(r0 + 2) * 24 + c0 + 0] = B.a20, J[(r0 + 2) * 24 + c0 + 1] = B.a21, J[(r0 + 2) * 24 + c0 + 2] = B.a22;
+            };
+            put(0, 0, -RiT);
+            put(0, 3, RiT * (-T));
+            put(0, 6, hat(RiT * (Pj - Pi - Vi * T - (0.5 * g) * T2)));
+            put(3, 3, -RiT);
+            put(3, 6, hat(RiT * (Vj - Vi - g * T)));
+            put(6, 6, ((-JrInv) * transpose(Rj)) * Ri);
+            const M3 ExpT = q_to_matrix(so3_inverse(so3_exp(rPhi)));
+            const M3 JrCorr = jacobian_r(JRg * dbg);
+            put(0, 9, -ldm3(M + VILBA_PI_JPG));
+            put(0, 12, -ldm3(M + VILBA_PI_JPA));
+            put(3, 9, -ldm3(M + VILBA_PI_JVG));
+            put(3, 12, -ldm3(M + VILBA_PI_JVA));
+            put(6, 9, (((-JrInv) * ExpT) * JrCorr) * JRg);
+            put(0, 15, RiT);
+            put(3, 18, RiT);
+            put(6, 21, JrInv);
+        }
+        __syncwarp();
+        const double wgt = misc[0];
+        for (int i = lane; i < 216; i += 32) {
+            const int r = i / 24, c = i - 24 * r;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s += Om[9 * r + k] * J[24 * k + c];
+            TJ[i] = wgt * s;
+        }
+        __syncwarp();
+        // bias edge (A = -I, B = +I): weights on the diagonal
+        V3 rg, ra;
+        bias_error(si, sj, rg, ra);
+        const double wg = w.inv_gyr_rw2 / M[VILBA_PI_DT], wa = w.inv_acc_rw2 / M[VILBA_PI_DT];
+        const double c2 = rg.x * (wg * rg.x) + rg.y * (wg * rg.y) + rg.z * (wg * rg.z) + ra.x * (wa * ra.x) +
+                          ra.y * (wa * ra.y) + ra.z * (wa * ra.z);
+        double brho0, brho1;
+        huber(c2, w.huber_bias, brho0, brho1);
+        const double eb[6] = {rg.x, rg.y, rg.z, ra.x, ra.y, ra.z};
+        // slot layout: 30 x 30 (local order PVR_i 9 | Bias_i 6 | PVR_j 9 | Bias_j 6) followed by 30 rhs entries
+        double* slot = w.imu_slot + 930 * (size_t)e;
+        for (int i = lane; i < 900; i += 32) {
+            const int r = i / 30, c = i - 30 * r;
+            double v = 0.0;
+            if (r < 24 && c < 24) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) v += J[24 * k + r] * TJ[24 * k + c];
+            }
+            // bias-edge blocks: (Bias_i,Bias_i) += w, (Bias_j,Bias_j) += w, (Bias_i,Bias_j) and transpose -= w
+            const int rb = (r >= 9 && r < 15) ? r - 9 : (r >= 24 ? r - 24 : -1);
+            const int cb = (c >= 9 && c < 15) ? c - 9 : (c >= 24 ? c - 24 : -1);
+            if (rb >= 0 && rb == cb) {
+                const double om = brho1 * (rb < 3 ? wg : wa);
+                const bool r_is_i = r < 15, c_is_i = c < 15;
+                v += (r_is_i == c_is_i) ? om : -om;
+            }
+            slot[i] = v;
+        }
+        if (lane < 30) {
+            const int r = lane;
+            double v = 0.0;
+            if (r < 24) {  // A^T * (-rho1 Omega e)
+#pragma unroll
+                for (int k = 0; k < 9; ++k) v -= J[24 * k + r] * (wgt * Oe[k]);
+            }
+            const int rb = (r >= 9 && r < 15) ? r - 9 : (r >= 24 ? r - 24 : -1);
+            if (rb >= 0) {
+                const double om = brho1 * (rb < 3 ? wg : wa);
+                const double omega_r = -om * eb[rb];
+                v += (r < 15) ? -omega_r : omega_r;  // A^T omega_r with A = -I ; B^T omega_r with B = +I
+            }
+            slot[900 + r] = v;
+        }
+        return;
+    }
+
+    // ======================= mono edges: one warp per map point =======================
+    const KfSmem ks = kf_smem_carve(smem, w.K);
+    const int warps_per_cta = blockDim.x >> 5;
+    double* acc_base = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + ((kf_smem_bytes(w.K) + 15) / 16) * 16);
+    const int nf = w.n_free;
+    double* acc = acc_base + (size_t)warp * nf * kAccStride;
+    for (int i = threadIdx.x; i < warps_per_cta * nf * kAccStride; i += blockDim.x) acc_base[i] = 0.0;
+    kf_stage<false>(w, ks, cur);
+    __syncthreads();
+    const int gwarp = blockIdx.x * warps_per_cta + warp;
+    const int nwarps = point_ctas * warps_per_cta;
+    const double* pts = w.pts[cur];
+    const M3 Rcb = ldm3(w.Rcb);
+    double maxd = 0.0;
+
+    for (int p = gwarp; p < w.P; p += nwarps) {
+        const int e0i = w.pt_obs_begin[p], e1i = w.pt_obs_begin[p + 1];
+        const V3 Pw = ld3(pts + 3 * (size_t)p);
+        double hxx = 0, hxy = 0, hxz = 0, hyy = 0, hyz = 0, hzz = 0, bx = 0, by = 0, bz = 0;
+        for (int base = e0i; base < e1i; base += 32) {
+            const int e = base + lane;
+            if (e < e1i) {
+                const MonoObs o = load_obs(w.obs, e);
+                double* Wp = w.W + 18 * (size_t)e;
+                const int blk = ks.blk[o.kf];
+                bool wrote_w = false;
+                if (!o.culled) {
+                    const double* cam = ks.cam + 12 * o.kf;
+                    double r0, r1;
+                    V3 Paux, Pc;
+                    mono_error(w, cam, Pw, o, r0, r1, Paux, Pc);
+                    const double is2 = (double)o.is2;
+                    double wgt = is2;
+                    if (o.robust) {
+                        double rho0, rho1;
+                        huber(r0 * (is2 * r0) + r1 * (is2 * r1), w.huber_mono, rho0, rho1);
+                        wgt = rho1 * is2;
+                    }
+                    const M3 Rcw = ldm3(cam);
+                    const double z = Pc.z;
+                    const double ja = w.fx / z, jb = (-Pc.x / z * w.fx) / z;
+                    const double jc = w.fy / z, jd = (-Pc.y / z * w.fy) / z;
+                    const double l00 = -(ja * Rcw.a00 + jb * Rcw.a20), l01 = -(ja * Rcw.a01 + jb * Rcw.a21),
+                                 l02 = -(ja * Rcw.a02 + jb * Rcw.a22);
+                    const double l10 = -(jc * Rcw.a10 + jd * Rcw.a20), l11 = -(jc * Rcw.a11 + jd * Rcw.a21),
+                                 l12 = -(jc * Rcw.a12 + jd * Rcw.a22);
+                    const M3 HR = hat(Paux) * Rcb;
+                    const double f00 = -(ja * HR.a00 + jb * HR.a20), f01 = -(ja * HR.a01 + jb * HR.a21),
+                                 f02 = -(ja * HR.a02 + jb * HR.a22);
+                    const double f10 = -(jc * HR.a10 + jd * HR.a20), f11 = -(jc * HR.a11 + jd * HR.a21),
+                                 f12 = -(jc * HR.a12 + jd * HR.a22);
+                    const double Jl[2][3] = {{l00, l01, l02}, {l10, l11, l12}};
+                    const double Jp[2][6] = {{-l00, -l01, -l02, f00, f01, f02}, {-l10, -l11, -l12, f10, f11, f12}};
+                    hxx += wgt * (l00 * l00 + l10 * l10);
+                    hxy += wgt * (l00 * l01 + l10 * l11);
+                    hxz += wgt * (l00 * l02 + l10 * l12);
+                    hyy += wgt * (l01 * l01 + l11 * l11);
+                    hyz += wgt * (l01 * l02 + l11 * l12);
+                    hzz += wgt * (l02 * l02 + l12 * l12);
+                    const double wr0 = -wgt * r0, wr1 = -wgt * r1;
+                    bx += l00 * wr0 + l10 * wr1;
+                    by += l01 * wr0 + l11 * wr1;
+                    bz += l02 * wr0 + l12 * wr1;
+                    if (blk >= 0) {
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                Wp[3 * r + c] = wgt * (Jp[0][r] * Jl[0][c] + Jp[1][r] * Jl[1][c]);
+                        wrote_w = true;
+                        // warp-private accumulation: the lanes of this warp hold distinct key-frames
+                        double* a = acc + (size_t)blk * kAccStride;
+                        int idx = 0;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                            for (int c = r; c < 6; ++c) {
+                                a[idx] += wgt * (Jp[0][r] * Jp[0][c] + Jp[1][r] * Jp[1][c]);
+                                ++idx;
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) a[21 + r] += Jp[0][r] * wr0 + Jp[1][r] * wr1;
+                    }
+                }
+                if (!wrote_w) {
+#pragma unroll
+                    for (int i = 0; i < 18; ++i) Wp[i] = 0.0;
+                }
+            }
+            __syncwarp();  // a point with more than 32 observations revisits no key-frame, but keep smem ordered
+        }
+        hxx = warp_sum(hxx), hxy = warp_sum(hxy), hxz = warp_sum(hxz);
+        hyy = warp_sum(hyy), hyz = warp_sum(hyz), hzz = warp_sum(hzz);
+        bx = warp_sum(bx), by = warp_sum(by), bz = warp_sum(bz);
+        if (lane == 0) {
+            double* H = w.Hll + 6 * (size_t)p;
+            H[0] = hxx, H[1] = hxy, H[2] = hxz, H[3] = hyy, H[4] = hyz, H[5] = hzz;
+            st3(w.bl + 3 * (size_t)p, v3(bx, by, bz));
+            maxd = fmax(maxd, fmax(fabs(hxx), fmax(fabs(hyy), fabs(hzz))));
+        }
+    }
+    maxd = warp_max(maxd);
+    if (lane == 0 && maxd > 0.0) atomic_max_nonneg(&w.lm->maxdiag_bits, maxd);  // max is order-independent
+    __syncthreads();
+    // CTA partial = fixed-order sum over its warps
+    double* part = w.lin_partial + (size_t)blockIdx.x * nf * kAccStride;
+    for (int i = threadIdx.x; i < nf * kAccStride; i += blockDim.x) {
+        double s = 0.0;
+        for (int ww = 0; ww < warps_per_cta; ++ww) s += acc_base[(size_t)ww * nf * kAccStride + i];
+        part[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// assemble: Hpp(r,c), r <= c, and bp from the CTA partials and the IMU slots (fixed order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pose6_index(int o) {  // offset inside a 15-block -> index in the [P,Phi] 6-block
+    return (o < 3) ? o : ((o >= 6 && o < 9) ? o - 3 : -1);
+}
+
+__global__ void __launch_bounds__(256) assemble_hpp_kernel(DevWindow w, int point_ctas) {
+    const int n = w.n, nf = w.n_free;
+    const size_t total = (size_t)n * n + n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const bool is_rhs = i >= (size_t)n * n;
+        int r, c;
+        if (is_rhs) {
+            r = (int)(i - (size_t)n * n);
+            c = r;
+        } else {
+            r = (int)(i / n);
+            c = (int)(i - (size_t)r * n);
+            if (r > c) {
+                w.Hpp[i] = 0.0;
+                continue;
+            }
+        }
+        const int a = r / 15, b = c / 15, oa = r - 15 * a, ob = c - 15 * b;
+        double v = 0.0;
+        // mono partials
+        const int pa = pose6_index(oa), pb = pose6_index(ob);
+        if (a == b && pa >= 0 && (is_rhs || pb >= 0)) {
+            int idx;
+            if (is_rhs)
+                idx = 21 + pa;
+            else  // upper index of (pa, pb), pa <= pb: rows of length 6,5,4,...
+                idx = pa * 6 - (pa * (pa - 1)) / 2 + (pb - pa);
+            const double* p = w.lin_partial + (size_t)a * kAccStride + idx;
+            for (int cta = 0; cta < point_ctas; ++cta) v += p[(size_t)cta * nf * kAccStride];
+        }
+        // IMU slots: the edge where block a is the "i" key-frame, then the one where it is the "j" key-frame
+        const int ea[2] = {w.blk_edge_i[a], w.blk_edge_j[a]};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int e = ea[s];
+            if (e < 0) continue;
+            const int bi = w.kf_block[w.imu_i[e]], bj = w.kf_block[w.imu_j[e]];
+            const int la = (a == bi) ? oa : 15 + oa;
+            int lb;
+            if (b == bi)
+                lb = ob;
+            else if (b == bj)
+                lb = 15 + ob;
+            else
+                continue;
+            if (a == b && ((a == bi) != (s == 0))) continue;  // safety: slot s must match the role of a
+            v += is_rhs ? w.imu_slot[930 * (size_t)e + 900 + la] : w.imu_slot[930 * (size_t)e + 30 * la + lb];
+        }
+        if (is_rhs)
+            w.bp[r] = v;
+        else
+            w.Hpp[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Schur gather: one CTA per key-frame block pair (a <= b)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSchurThreads = 128;
+
+__global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(DevWindow w) {
+    __shared__ double red[kSchurThreads / 32][42];
+    __shared__ double blockacc[42];
+    const int pair = blockIdx.x;
+    const int a = w.pair_a[pair], b = w.pair_b[pair];
+    const int t0 = w.pair_begin[pair], t1 = w.pair_begin[pair + 1];
+    const double lambda = w.lm->lambda;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool diag = (a == b);
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+    double rb[6] = {0, 0, 0, 0, 0, 0};
+    for (int t = t0 + (int)threadIdx.x; t < t1; t += kSchurThreads) {
+        const int ea = w.pair_ea[t], eb = w.pair_eb[t];
+        const int p = w.edge_pt[ea];
+        const double* H = w.Hll + 6 * (size_t)p;
+        bool ok;
+        const S3 Dinv = s3_inverse(S3{H[0] + lambda, H[1], H[2], H[3] + lambda, H[4], H[5] + lambda}, ok);
+        const double* Wa = w.W + 18 * (size_t)ea;
+        const double* Wb = w.W + 18 * (size_t)eb;
+        double Y[18], B[18];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const V3 yv = s3_mul(Dinv, v3(Wa[3 * r], Wa[3 * r + 1], Wa[3 * r + 2]));  // Y = W_a Dinv
+            Y[3 * r] = yv.x, Y[3 * r + 1] = yv.y, Y[3 * r + 2] = yv.z;
+        }
+#pragma unroll
+        for (int i = 0; i < 18; ++i) B[i] = Wb[i];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                acc[6 * r + c] += Y[3 * r] * B[3 * c] + Y[3 * r + 1] * B[3 * c + 1] + Y[3 * r + 2] * B[3 * c + 2];
+        if (diag) {  // ea == eb: rhs   bs(a) -= W_a Dinv b_l
+            const V3 bl = ld3(w.bl + 3 * (size_t)p);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) rb[r] += Y[3 * r] * bl.x + Y[3 * r + 1] * bl.y + Y[3 * r + 2] * bl.z;
+        }
+    }
+    // fixed reduction tree: lanes (xor shuffles), then warps in order
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = warp_sum(acc[i]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rb[i] = warp_sum(rb[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) red[warp][i] = acc[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) red[warp][36 + i] = rb[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 42) {
+        double s = 0.0;
+        for (int ww = 0; ww < kSchurThreads / 32; ++ww) s += red[ww][threadIdx.x];
+        blockacc[threadIdx.x] = s;
+    }
+    __syncthreads();
+    // write the 15x15 block of S (upper part of the matrix): S = Hpp + lambda I - scatter(acc)
+    const int n = w.n;
+    for (int i = threadIdx.x; i < 225; i += kSchurThreads) {
+        const int r = i / 15, c = i - 15 * r;
+        const int gr = 15 * a + r, gc = 15 * b + c;
+        if (gr > gc) continue;
+        double v = w.Hpp[(size_t)gr * n + gc];
+        if (gr == gc) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
+        const int pr = pose6_index(r), pc = pose6_index(c);
+        if (pr >= 0 && pc >= 0) v -= blockacc[6 * pr + pc];
+        w.S[(size_t)gr * n + gc] = v;
+    }
+    if (diag && threadIdx.x < 15) {
+        const int r = threadIdx.x;
+        double v = w.bp[15 * a + r];
+        const int pr = pose6_index(r);
+        if (pr >= 0) v -= blockacc[36 + pr];
+        w.bs[15 * a + r] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_linearize_v2(cudaStream_t s, const DevWindow& w, int point_ctas) {
+    const int warps = kPointThreads / 32;
+    size_t sm = linearize_v2_smem_bytes(w.K, w.n_free, warps);
+    const size_t imu_sm = sizeof(double) * (216 + 81 + 216 + 9 + 9 + 8);
+    if (sm < imu_sm) sm = imu_sm;
+    static size_t configured = 0;
+    if (sm > configured) {
+        cudaError_t e = cudaFuncSetAttribute(linearize_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        configured = sm;
+    }
+    linearize_v2_kernel<<<point_ctas + w.NI, kPointThreads, sm, s>>>(w, point_ctas);
+    const size_t total = (size_t)w.n * w.n + w.n;
+    int g = (int)((total + 255) / 256);
+    if (g > 592) g = 592;
+    assemble_hpp_kernel<<<g, 256, 0, s>>>(w, point_ctas);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_schur_gather(cudaStream_t s, const DevWindow& w) {
+    schur_gather_kernel<<<w.n_pairs, kSchurThreads, 0, s>>>(w);
+    return cudaGetLastError();
+}
+
+}  // namespace vilba

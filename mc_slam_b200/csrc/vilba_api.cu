@@ -63,13 +63,14 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // offsets of one window inside the device arena
 struct Layout {
     // input section (one H2D copy)
-    size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, input_end;
+    size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, blk_edge_i, blk_edge_j, edge_pt,
+        pair_a, pair_b, pair_begin, pair_ea, pair_eb, input_end;
     // work section
-    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, S, Lfac, bs, x, lm, n_culled,
+    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, S, Lfac, cdinv, bs, x, lm, dbg, n_culled,
         outlier, total;
 };
 
-Layout make_layout(int K, int NI, int P, int E, int n) {
+Layout make_layout(int K, int NI, int P, int E, int n, int n_free, int n_pairs, size_t n_triples, int lin_ctas) {
     Layout L;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -85,6 +86,14 @@ Layout make_layout(int K, int NI, int P, int E, int n) {
     L.kf_block = take(sizeof(int) * (size_t)K);
     L.imu_i = take(sizeof(int) * (size_t)NI);
     L.imu_j = take(sizeof(int) * (size_t)NI);
+    L.blk_edge_i = take(sizeof(int) * (size_t)n_free);
+    L.blk_edge_j = take(sizeof(int) * (size_t)n_free);
+    L.edge_pt = take(sizeof(int) * (size_t)E);
+    L.pair_a = take(sizeof(int) * (size_t)n_pairs);
+    L.pair_b = take(sizeof(int) * (size_t)n_pairs);
+    L.pair_begin = take(sizeof(int) * ((size_t)n_pairs + 1));
+    L.pair_ea = take(sizeof(int) * n_triples);
+    L.pair_eb = take(sizeof(int) * n_triples);
     L.input_end = o;
     for (int b = 0; b < 2; ++b) L.kf_state[b] = take(sizeof(double) * 22 * (size_t)K);
     for (int b = 0; b < 2; ++b) L.pts[b] = take(sizeof(double) * 3 * (size_t)P);
@@ -97,11 +106,15 @@ Layout make_layout(int K, int NI, int P, int E, int n) {
     L.Hll = take(sizeof(double) * 6 * (size_t)P);
     L.bl = take(sizeof(double) * 3 * (size_t)P);
     L.W = take(sizeof(double) * 18 * (size_t)E);
+    L.lin_partial = take(sizeof(double) * 27 * (size_t)n_free * lin_ctas);
+    L.imu_slot = take(sizeof(double) * 930 * (size_t)NI);
     L.S = take(sizeof(double) * (size_t)n * n);
     L.Lfac = take(sizeof(double) * (size_t)n * n);
+    L.cdinv = take(sizeof(double) * (size_t)n);
     L.bs = take(sizeof(double) * (size_t)n);
     L.x = take(sizeof(double) * (size_t)n);
     L.lm = take(sizeof(LmState));
+    L.dbg = take(sizeof(long long) * 16);
     L.n_culled = take(sizeof(int) * 4);
     L.outlier = take((size_t)E);
     L.total = o;
@@ -128,6 +141,8 @@ struct vilba_ctx {
     // stats
     vilba_stats stats;
     bool profiling = false;
+    int lin_ctas = 1;
+    bool use_v1 = false;   // env VILBA_V1=1: atomic-based accumulation kernels (kept for A/B)
     int chol_cluster = 8;  // CTAs in the Cholesky cluster (0 = v1 single-CTA kernel); env VILBA_CHOL_CLUSTER
     std::vector<cudaEvent_t> prof_events;  // pairs, drained at sync points
     std::vector<int> prof_kind;
@@ -220,7 +235,59 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     for (int k = 0; k < K; ++k)
         if (!(w->kf_flags[k] & VILBA_KF_FIXED)) kf_block[k] = n_free++;
     const int n = 15 * n_free;
-    const Layout L = make_layout(K, NI, P, E, n);
+    // v2 accumulation structures: IMU edge of every block, map point of every edge, and per key-frame
+    // block pair (a <= b) the list of (edge_a, edge_b) that share a map point
+    std::vector<int> blk_edge_i(n_free, -1), blk_edge_j(n_free, -1);
+    for (int e = 0; e < NI; ++e) {
+        const int bi = kf_block[w->imu_kf_i[e]], bj = kf_block[w->imu_kf_j[e]];
+        if ((bi >= 0 && blk_edge_i[bi] >= 0) || (bj >= 0 && blk_edge_j[bj] >= 0) || (bi >= 0 && bi == bj)) {
+            ctx->err = "a key-frame may start / end at most one IMU edge";
+            return VILBA_ERR_ARG;
+        }
+        if (bi >= 0) blk_edge_i[bi] = e;
+        if (bj >= 0) blk_edge_j[bj] = e;
+    }
+    const int n_pairs = n_free * (n_free + 1) / 2;
+    auto pair_index = [n_free](int a, int b) { return a * n_free - a * (a - 1) / 2 + (b - a); };
+    std::vector<int> edge_pt(E), pair_a(n_pairs), pair_b(n_pairs), pair_begin(n_pairs + 1, 0);
+    for (int a = 0; a < n_free; ++a)
+        for (int b = a; b < n_free; ++b) pair_a[pair_index(a, b)] = a, pair_b[pair_index(a, b)] = b;
+    for (int p = 0; p < P; ++p)
+        for (int ei = w->pt_obs_begin[p]; ei < w->pt_obs_begin[p + 1]; ++ei) {
+            edge_pt[ei] = p;
+            const int bi = kf_block[w->obs_kf[ei]];
+            if (bi < 0) continue;
+            for (int ej = ei; ej < w->pt_obs_begin[p + 1]; ++ej) {
+                const int bj = kf_block[w->obs_kf[ej]];
+                if (bj < 0) continue;
+                if (ej != ei && bi == bj) {
+                    ctx->err = "a map point is observed twice by the same key-frame";
+                    return VILBA_ERR_ARG;
+                }
+                pair_begin[pair_index(bi < bj ? bi : bj, bi < bj ? bj : bi) + 1]++;
+            }
+        }
+    for (int i = 0; i < n_pairs; ++i) pair_begin[i + 1] += pair_begin[i];
+    const size_t n_triples = (size_t)pair_begin[n_pairs];
+    std::vector<int> pair_ea(n_triples), pair_eb(n_triples), fill(pair_begin.begin(), pair_begin.end() - 1);
+    for (int p = 0; p < P; ++p)
+        for (int ei = w->pt_obs_begin[p]; ei < w->pt_obs_begin[p + 1]; ++ei) {
+            const int bi = kf_block[w->obs_kf[ei]];
+            if (bi < 0) continue;
+            for (int ej = ei; ej < w->pt_obs_begin[p + 1]; ++ej) {
+                const int bj = kf_block[w->obs_kf[ej]];
+                if (bj < 0) continue;
+                const bool sw = bj < bi;
+                const int slot = fill[pair_index(sw ? bj : bi, sw ? bi : bj)]++;
+                pair_ea[slot] = sw ? ej : ei;
+                pair_eb[slot] = sw ? ei : ej;
+            }
+        }
+    const int warps_per_cta_lin = kPointThreads / 32;
+    int lin_ctas = (P + warps_per_cta_lin - 1) / warps_per_cta_lin;
+    if (lin_ctas > 2 * ctx->sm_count) lin_ctas = 2 * ctx->sm_count;
+    if (lin_ctas < 1) lin_ctas = 1;
+    const Layout L = make_layout(K, NI, P, E, n, n_free, n_pairs, n_triples, lin_ctas);
     CK(ctx->arena.reserve(L.total), "cudaMalloc(arena)");
     CK(ctx->pinned.reserve(L.input_end), "cudaMallocHost(staging)");
     char* h = ctx->pinned.base;
@@ -242,6 +309,16 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     if (NI) {
         std::memcpy(h + L.imu_i, w->imu_kf_i, sizeof(int) * (size_t)NI);
         std::memcpy(h + L.imu_j, w->imu_kf_j, sizeof(int) * (size_t)NI);
+    }
+    std::memcpy(h + L.blk_edge_i, blk_edge_i.data(), sizeof(int) * (size_t)n_free);
+    std::memcpy(h + L.blk_edge_j, blk_edge_j.data(), sizeof(int) * (size_t)n_free);
+    if (E) std::memcpy(h + L.edge_pt, edge_pt.data(), sizeof(int) * (size_t)E);
+    std::memcpy(h + L.pair_a, pair_a.data(), sizeof(int) * (size_t)n_pairs);
+    std::memcpy(h + L.pair_b, pair_b.data(), sizeof(int) * (size_t)n_pairs);
+    std::memcpy(h + L.pair_begin, pair_begin.data(), sizeof(int) * ((size_t)n_pairs + 1));
+    if (n_triples) {
+        std::memcpy(h + L.pair_ea, pair_ea.data(), sizeof(int) * n_triples);
+        std::memcpy(h + L.pair_eb, pair_eb.data(), sizeof(int) * n_triples);
     }
     char* d = ctx->arena.base;
     CK(cudaMemcpyAsync(d, h, L.input_end, cudaMemcpyHostToDevice, ctx->stream), "H2D window");
@@ -267,11 +344,25 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     dw.Hll = reinterpret_cast<double*>(d + L.Hll);
     dw.bl = reinterpret_cast<double*>(d + L.bl);
     dw.W = reinterpret_cast<double*>(d + L.W);
+    dw.lin_partial = reinterpret_cast<double*>(d + L.lin_partial);
+    dw.imu_slot = reinterpret_cast<double*>(d + L.imu_slot);
+    dw.blk_edge_i = reinterpret_cast<const int*>(d + L.blk_edge_i);
+    dw.blk_edge_j = reinterpret_cast<const int*>(d + L.blk_edge_j);
+    dw.edge_pt = reinterpret_cast<const int*>(d + L.edge_pt);
+    dw.n_pairs = n_pairs;
+    dw.pair_a = reinterpret_cast<const int*>(d + L.pair_a);
+    dw.pair_b = reinterpret_cast<const int*>(d + L.pair_b);
+    dw.pair_begin = reinterpret_cast<const int*>(d + L.pair_begin);
+    dw.pair_ea = reinterpret_cast<const int*>(d + L.pair_ea);
+    dw.pair_eb = reinterpret_cast<const int*>(d + L.pair_eb);
+    ctx->lin_ctas = lin_ctas;
     dw.S = reinterpret_cast<double*>(d + L.S);
     dw.Lfac = reinterpret_cast<double*>(d + L.Lfac);
+    dw.cdinv = reinterpret_cast<double*>(d + L.cdinv);
     dw.bs = reinterpret_cast<double*>(d + L.bs);
     dw.x = reinterpret_cast<double*>(d + L.x);
     dw.lm = reinterpret_cast<LmState*>(d + L.lm);
+    dw.dbg = reinterpret_cast<long long*>(d + L.dbg);
     dw.fx = w->fx, dw.fy = w->fy, dw.cx = w->cx, dw.cy = w->cy;
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) dw.Rcb[3 * r + c] = w->Rbc[3 * c + r];  // Rcb = Rbc^T
@@ -323,6 +414,15 @@ int reset_window(vilba_ctx* ctx) {
     }
     CK(cudaMemsetAsync(d + L.lm, 0, sizeof(LmState), s), "reset lm");
     CK(cudaMemsetAsync(d + L.n_culled, 0, sizeof(int) * 4, s), "reset counters");
+    if (std::getenv("VILBA_DEBUG_COUNTERS")) {
+        long long h[16];
+        if (cudaMemcpy(h, d + L.dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[8] > 0) {
+            std::fprintf(stderr, "[vilba dbg] chol calls=%lld avg cycles/phase:", h[8]);
+            for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %lld", h[i] / h[8]);
+            std::fprintf(stderr, "\n");
+        }
+        CK(cudaMemsetAsync(d + L.dbg, 0, sizeof(long long) * 16, s), "reset dbg");
+    }
     return VILBA_OK;
 }
 
@@ -352,7 +452,10 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, int n_active, vilba_res
     bool ok = true;
     for (int it = 0; it < iterations && !stop_requested(stop_flag) && ok; ++it) {
         prof_begin(ctx, 0);
-        CK(launch_linearize(s, dw, ctx->cfg), "linearize");
+        if (ctx->use_v1)
+            CK(launch_linearize(s, dw, ctx->cfg), "linearize");
+        else
+            CK(launch_linearize_v2(s, dw, ctx->lin_ctas), "linearize_v2");
         prof_end(ctx);
         CK(launch_lm_iter_begin(s, dw, it), "lm_iter_begin");
         stt.kernel_launches += 2 + (dw.NI > 0 ? 1 : 0);
@@ -360,7 +463,10 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, int n_active, vilba_res
         LmState lm;
         do {
             prof_begin(ctx, 1);
-            CK(launch_schur(s, dw, ctx->cfg), "schur");
+            if (ctx->use_v1)
+                CK(launch_schur(s, dw, ctx->cfg), "schur");
+            else
+                CK(launch_schur_gather(s, dw), "schur_gather");
             prof_end(ctx);
             prof_begin(ctx, 2);
             if (ctx->chol_cluster > 0)
@@ -518,6 +624,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::atoi(e);
+    if (const char* e = std::getenv("VILBA_V1")) ctx->use_v1 = std::atoi(e) != 0;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
         std::fprintf(stderr, "vilba_create: %s\n", cudaGetErrorString(cudaGetLastError()));
