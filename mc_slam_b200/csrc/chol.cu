@@ -109,7 +109,9 @@ __device__ __forceinline__ bool warp_ldlt16_mb4(double (&a)[NB], int lane, doubl
 
 }  // namespace
 
-__global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(DevWindow w) {
+__global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = *wp;
+    if (w.lm->phase != PH_TRIAL) return;  // uniform over the cluster: nobody reaches a cluster barrier
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int csize = (int)cluster.num_blocks();
@@ -380,38 +382,32 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(DevWindow w)
 #endif
 }
 
-static size_t chol_cluster_smem(int n) {
+size_t chol_smem_bytes(int n) {
     return sizeof(double) * ((size_t)NB * NB + (size_t)(n + 8) * LDP + (size_t)n + 2 * NB + 80);
 }
 
-cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow& w, int cluster_size) {
-    const size_t sm = chol_cluster_smem(w.n);
-    static size_t configured = 0;
-    static bool nonportable = false;
-    cudaError_t e;
-    if (sm > configured) {
-        e = cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        configured = sm;
-    }
-    if (cluster_size > 8 && !nonportable) {
+cudaError_t configure_chol(const LaunchDims& d) {
+    cudaError_t e = cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_chol);
+    if (e != cudaSuccess) return e;
+    if (d.chol_cluster > 8)
         e = cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
-        nonportable = true;
-    }
+    return e;
+}
+
+cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cluster_size, 1, 1);
+    cfg.gridDim = dim3(d.chol_cluster, 1, 1);
     cfg.blockDim = dim3(kCholThreads, 1, 1);
-    cfg.dynamicSmemBytes = sm;
+    cfg.dynamicSmemBytes = d.smem_chol;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.x = d.chol_cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, chol_cluster_kernel, w);
+    return cudaLaunchKernelEx(&cfg, chol_cluster_kernel, wp);
 }
 
 }  // namespace vilba

@@ -12,6 +12,8 @@ constexpr int kPointThreads = 256;  // 8 warps per CTA, one warp per map point
 constexpr int kCholThreads = 512;
 constexpr int kCholNB = 16;
 constexpr int kMaxKF = 256;          // key-frames per window supported by the shared-memory stage
+constexpr int kPointGridPerSM = 2;   // CTAs per SM of the grid-stride per-point kernels (fixed grid => graph-capturable)
+constexpr int kImuGrid = 64;         // CTAs (one warp each) of the per-IMU-edge kernels, grid-stride
 
 // obs record: 16 bytes, one vector load per mono edge.
 //   x = bits of float u, y = bits of float v, z = bits of float invSigma2,
@@ -22,6 +24,13 @@ constexpr int OBS_ROBUST = 1 << 25;  // edge still has its Huber  (Optimizer.cpp
 
 // Device-resident Levenberg-Marquardt controller state
 // (members of OptimizationAlgorithmLevenberg, optimization_algorithm_levenberg.cpp:41-60)
+enum LmPhase { PH_LINEARIZE = 0, PH_TRIAL = 1, PH_DONE = 2 };
+
+struct IterRec {  // one outer LM iteration, written by the device-side controller
+    int stage, iteration, trials, result, n_active, accepted;
+    double chi0, chi1, lambda, lambda_first;
+};
+
 struct LmState {
     double lambda;        // _currentLambda
     double ni;            // _ni
@@ -40,7 +49,16 @@ struct LmState {
     int accepted;         // last trial accepted
     int iter_result;      // -1 running, 0 OK, 1 Terminate
     int stop;             // force-stop flag mirrored from the host
-    int pad;
+    // device-side control flow: the host enqueues "slots" (linearise-if-needed + one LM trial + decide)
+    // without synchronising; every kernel looks at `phase` and returns early when it has nothing to do
+    int phase;            // LmPhase
+    int iter;             // outer iteration inside the current optimize() call
+    int max_iters;        // iterations of the current optimize() call
+    int stage;            // 1 or 2
+    int n_active;         // active edges of the stage (mono + 2 per IMU pair)
+    int n_culled;         // edges moved to level 1 by the cull
+    int n_trace;
+    IterRec trace[VILBA_MAX_TRACE];
 };
 
 struct DevWindow {
@@ -73,6 +91,8 @@ struct DevWindow {
     // v2 (atomic-free) accumulation
     double* lin_partial;     // lin_ctas * n_free * 27   per-CTA partial pose blocks of the mono edges
     double* imu_slot;        // NI * 930                 30x30 block + 30 rhs of every IMU edge pair
+    double* mono_sum;        // n_free * 27              fixed-order sum of the CTA partials
+    double* Y;               // E * 24                   per trial: W D^-1 (18) and W (D^-1 b_l) (6)
     const int* blk_edge_i;   // n_free: IMU edge in which the block is key-frame i, or -1
     const int* blk_edge_j;   // n_free: IMU edge in which the block is key-frame j, or -1
     const int* edge_pt;      // E: map point of every mono edge
@@ -103,25 +123,32 @@ cudaError_t launch_preint_batch(cudaStream_t stream, int n_pairs, const int* sam
                                 double* out, double gyr_cov, double acc_cov, int group);
 
 // ---- local BA ------------------------------------------------------------------------------------
-struct LaunchCfg {
-    int point_grid;   // CTAs of the per-point kernels
+// All kernels take a pointer to the device-resident DevWindow, so that their launch parameters do not
+// change between windows and one LM "slot" can be captured once in a CUDA graph.
+struct LaunchDims {
     int sm_count;
+    int point_grid;       // kPointGridPerSM * sm_count
+    int chol_cluster;     // CTAs of the Cholesky cluster
+    size_t smem_point;    // dynamic shared memory of update_eval / flags
+    size_t smem_lin;      // ... of linearize_v2
+    size_t smem_chol;     // ... of chol_cluster
 };
+size_t point_smem_bytes(int K);
+size_t linearize_smem_bytes(int K, int n_free);
+size_t chol_smem_bytes(int n);
+cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels
 
-cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow& w);
-// evaluate (and optionally first apply x to) the estimates; accumulates robust chi2 into lm->chi_acc
-cudaError_t launch_update_eval(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, bool apply);
-cudaError_t launch_linearize(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
-cudaError_t launch_schur(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg);
-cudaError_t launch_linearize_v2(cudaStream_t s, const DevWindow& w, int point_ctas);
-cudaError_t launch_schur_gather(cudaStream_t s, const DevWindow& w);
-cudaError_t launch_chol_solve(cudaStream_t s, const DevWindow& w);           // v1 single-CTA kernel (kept for A/B)
-cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow& w, int cluster_size);
-// LM bookkeeping kernels (single CTA)
-cudaError_t launch_lm_stage_begin(cudaStream_t s, const DevWindow& w);   // current_chi = chi_acc
-cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow& w, int iteration);
-cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow& w);
-cudaError_t launch_cull(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, int* n_culled_dev);
-cudaError_t launch_final_flags(cudaStream_t s, const DevWindow& w, const LaunchCfg& cfg, uint8_t* outlier);
+cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp);
+cudaError_t launch_eval_initial(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);  // eval at the current state
+cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, int stage, int max_iters);
+// one slot = [linearize (mono | imu on `side`) -> reduce -> assemble -> iter_begin] if phase == LINEARIZE,
+//            [schur prep -> gather -> cholesky -> update+eval -> decide] if phase == TRIAL
+// `probe` (6 timing events, or NULL): [0,1] linearize+reduce+assemble, [2,3] Schur prep+gather, [3,4] Cholesky,
+// [4,5] update+eval
+cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, const DevWindow* wp,
+                        const LaunchDims& d, cudaEvent_t* probe);
+cudaError_t launch_cull(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d, uint8_t* outlier);
+constexpr int kKernelsPerSlot = 10;
 
 }  // namespace vilba

@@ -23,22 +23,19 @@ size_t linearize_v2_smem_bytes(int K, int n_free, int warps) {
     return kf_smem_bytes(K) + sizeof(double) * (size_t)warps * n_free * kAccStride + 16;
 }
 
-__global__ void __launch_bounds__(kPointThreads) linearize_v2_kernel(DevWindow w, int point_ctas) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(32) linearize_imu_v2_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = *wp;
+    if (w.lm->phase != PH_LINEARIZE) return;
+    // one warp per IMU edge pair (EdgeNavStatePVR + EdgeNavStateBias)
+    __shared__ double J[216];   // 9 x 24: PVR_i (9) | Bias_i (6) | PVR_j (9)
+    __shared__ double Om[81];
+    __shared__ double TJ[216];  // 9 x 24  (rho1 Omega) J
+    __shared__ double ev[9];
+    __shared__ double Oe[9];    // Omega e
+    __shared__ double misc[2];  // [0] rho1
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int cur = w.lm->cur;
-
-    if ((int)blockIdx.x >= point_ctas) {
-        // ======================= IMU edge pair (warp 0 of the CTA) =======================
-        if (warp != 0) return;
-        double* J = smem;            // 9 x 24: PVR_i (9) | Bias_i (6) | PVR_j (9)
-        double* Om = J + 216;        // 81
-        double* TJ = Om + 81;        // 9 x 24  (rho1 Omega) J
-        double* ev = TJ + 216;       // 9
-        double* Oe = ev + 9;         // 9   Omega e
-        double* misc = Oe + 9;       // [0] rho1
-        const int e = blockIdx.x - point_ctas;
+    for (int e = blockIdx.x; e < w.NI; e += gridDim.x) {
         const int ki = w.imu_i[e], kj = w.imu_j[e];
         const double* si = w.kf_state[cur] + 22 * (size_t)ki;
         const double* sj = w.kf_state[cur] + 22 * (size_t)kj;
@@ -51,14 +48,6 @@ __global__ void __launch_bounds__(kPointThreads) linearize_v2_kernel(DevWindow w
             pvr_error(w, si, sj, M, rP, rV, rPhi);
             ev[0] = rP.x, ev[1] = rP.y, ev[2] = rP.z, ev[3] = rV.x, ev[4] = rV.y, ev[5] = rV.z;
             ev[6] = rPhi.x, ev[7] = rPhi.y, ev[8] = rPhi.z;
-            double rho0, rho1;
-            huber(quad9(Om, ev), w.huber_pvr, rho0, rho1);
-            misc[0] = rho1;
-            for (int r = 0; r < 9; ++r) {
-                double t = 0.0;
-                for (int c = 0; c < 9; ++c) t += Om[9 * r + c] * ev[c];
-                Oe[r] = t;
-            }
             const V3 Pi = ld3(si), Vi = ld3(si + 3), Pj = ld3(sj), Vj = ld3(sj + 3);
             const M3 Ri = q_to_matrix(Q4{si[6], si[7], si[8], si[9]});
             const M3 Rj = q_to_matrix(Q4{sj[6], sj[7], sj[8], sj[9]});
@@ -89,6 +78,22 @@ __global__ void __launch_bounds__(kPointThreads) linearize_v2_kernel(DevWindow w
             put(0, 15, RiT);
             put(3, 18, RiT);
             put(6, 21, JrInv);
+        }
+        __syncwarp();
+        if (lane < 9) {  // Omega e, then chi2 = e^T Omega e and the Huber weight
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) t += Om[9 * lane + c] * ev[c];
+            Oe[lane] = t;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double c2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 9; ++r) c2 += ev[r] * Oe[r];
+            double rho0, rho1;
+            huber(c2, w.huber_pvr, rho0, rho1);
+            misc[0] = rho1;
         }
         __syncwarp();
         const double wgt = misc[0];
@@ -143,8 +148,18 @@ __global__ void __launch_bounds__(kPointThreads) linearize_v2_kernel(DevWindow w
             }
             slot[900 + r] = v;
         }
-        return;
+        __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = *wp;
+    if (w.lm->phase != PH_LINEARIZE) return;
+    const int point_ctas = gridDim.x;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cur = w.lm->cur;
 
     // ======================= mono edges: one warp per map point =======================
     const KfSmem ks = kf_smem_carve(smem, w.K);
@@ -267,8 +282,25 @@ __device__ __forceinline__ int pose6_index(int o) {  // offset inside a 15-block
     return (o < 3) ? o : ((o >= 6 && o < 9) ? o - 3 : -1);
 }
 
-__global__ void __launch_bounds__(256) assemble_hpp_kernel(DevWindow w, int point_ctas) {
-    const int n = w.n, nf = w.n_free;
+// fixed-order reduction of the CTA partials: one warp per entry (lane-strided partial sums, xor tree)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const DevWindow* __restrict__ wp, int point_ctas) {
+    const DevWindow w = *wp;
+    if (w.lm->phase != PH_LINEARIZE) return;
+    const int entries = w.n_free * kAccStride;
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gw < entries; gw += nw) {
+        double s = 0.0;
+        for (int cta = lane; cta < point_ctas; cta += 32) s += w.lin_partial[(size_t)cta * entries + gw];
+        s = warp_sum(s);
+        if (lane == 0) w.mono_sum[gw] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) assemble_hpp_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = *wp;
+    if (w.lm->phase != PH_LINEARIZE) return;
+    const int n = w.n;
     const size_t total = (size_t)n * n + n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const bool is_rhs = i >= (size_t)n * n;
@@ -294,8 +326,7 @@ __global__ void __launch_bounds__(256) assemble_hpp_kernel(DevWindow w, int poin
                 idx = 21 + pa;
             else  // upper index of (pa, pb), pa <= pb: rows of length 6,5,4,...
                 idx = pa * 6 - (pa * (pa - 1)) / 2 + (pb - pa);
-            const double* p = w.lin_partial + (size_t)a * kAccStride + idx;
-            for (int cta = 0; cta < point_ctas; ++cta) v += p[(size_t)cta * nf * kAccStride];
+            v += w.mono_sum[(size_t)a * kAccStride + idx];
         }
         // IMU slots: the edge where block a is the "i" key-frame, then the one where it is the "j" key-frame
         const int ea[2] = {w.blk_edge_i[a], w.blk_edge_j[a]};
@@ -325,58 +356,78 @@ __global__ void __launch_bounds__(256) assemble_hpp_kernel(DevWindow w, int poin
 // ------------------------------------------------------------------------------------------------
 // Schur gather: one CTA per key-frame block pair (a <= b)
 // ------------------------------------------------------------------------------------------------
-constexpr int kSchurThreads = 128;
+constexpr int kSchurThreads = 1024;  // 32 warps x 5 (edge_a, edge_b) pairs per pass
 
-__global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(DevWindow w) {
+// per trial: Y_e = W_e D_l^-1 (BDinv, block_solver.hpp:407) and Wc_e = W_e (D_l^-1 b_l) for every mono edge
+__global__ void __launch_bounds__(256) schur_prep_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = *wp;
+    if (w.lm->phase != PH_TRIAL) return;
+    const double lambda = w.lm->lambda;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < w.E; e += gridDim.x * blockDim.x) {
+        const int p = w.edge_pt[e];
+        const double* H = w.Hll + 6 * (size_t)p;
+        bool ok;
+        const S3 Dinv = s3_inverse(S3{H[0] + lambda, H[1], H[2], H[3] + lambda, H[4], H[5] + lambda}, ok);
+        const V3 db = s3_mul(Dinv, ld3(w.bl + 3 * (size_t)p));
+        const double* Wp = w.W + 18 * (size_t)e;
+        double* Yp = w.Y + 24 * (size_t)e;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const V3 wr = v3(Wp[3 * r], Wp[3 * r + 1], Wp[3 * r + 2]);
+            const V3 yv = s3_mul(Dinv, wr);
+            Yp[3 * r] = yv.x, Yp[3 * r + 1] = yv.y, Yp[3 * r + 2] = yv.z;
+            Yp[18 + r] = dot(wr, db);
+        }
+    }
+}
+
+// Lane mapping: a warp handles 5 list entries per pass, 6 lanes each; lane (slot, r) owns row r of the
+// 6x6 product Y_a W_b^T of its entry, so the 6 lanes of an entry read Y_a (144 B) and W_b (144 B) as
+// coalesced, L1-broadcast lines instead of 42 scattered 8-byte loads per thread.
+__global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = *wp;
+    if (w.lm->phase != PH_TRIAL) return;
     __shared__ double red[kSchurThreads / 32][42];
     __shared__ double blockacc[42];
-    const int pair = blockIdx.x;
+    for (int pair = blockIdx.x; pair < w.n_pairs; pair += gridDim.x) {
     const int a = w.pair_a[pair], b = w.pair_b[pair];
     const int t0 = w.pair_begin[pair], t1 = w.pair_begin[pair + 1];
     const double lambda = w.lm->lambda;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool diag = (a == b);
-    double acc[36];
+    const int slot = lane / 6, r = lane - 6 * slot;  // lanes 30, 31 idle
+    const bool live = lane < 30;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    double rb = 0.0;
+    constexpr int kPerPass = (kSchurThreads / 32) * 5;
+    if (live) {
+        for (int t = t0 + warp * 5 + slot; t < t1; t += kPerPass) {
+            const int ea = w.pair_ea[t], eb = w.pair_eb[t];
+            const double* Ya = w.Y + 24 * (size_t)ea;
+            const double* Wb = w.W + 18 * (size_t)eb;
+            const double y0 = Ya[3 * r], y1 = Ya[3 * r + 1], y2 = Ya[3 * r + 2];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-    double rb[6] = {0, 0, 0, 0, 0, 0};
-    for (int t = t0 + (int)threadIdx.x; t < t1; t += kSchurThreads) {
-        const int ea = w.pair_ea[t], eb = w.pair_eb[t];
-        const int p = w.edge_pt[ea];
-        const double* H = w.Hll + 6 * (size_t)p;
-        bool ok;
-        const S3 Dinv = s3_inverse(S3{H[0] + lambda, H[1], H[2], H[3] + lambda, H[4], H[5] + lambda}, ok);
-        const double* Wa = w.W + 18 * (size_t)ea;
-        const double* Wb = w.W + 18 * (size_t)eb;
-        double Y[18], B[18];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const V3 yv = s3_mul(Dinv, v3(Wa[3 * r], Wa[3 * r + 1], Wa[3 * r + 2]));  // Y = W_a Dinv
-            Y[3 * r] = yv.x, Y[3 * r + 1] = yv.y, Y[3 * r + 2] = yv.z;
-        }
-#pragma unroll
-        for (int i = 0; i < 18; ++i) B[i] = Wb[i];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int c = 0; c < 6; ++c)
-                acc[6 * r + c] += Y[3 * r] * B[3 * c] + Y[3 * r + 1] * B[3 * c + 1] + Y[3 * r + 2] * B[3 * c + 2];
-        if (diag) {  // ea == eb: rhs   bs(a) -= W_a Dinv b_l
-            const V3 bl = ld3(w.bl + 3 * (size_t)p);
-#pragma unroll
-            for (int r = 0; r < 6; ++r) rb[r] += Y[3 * r] * bl.x + Y[3 * r + 1] * bl.y + Y[3 * r + 2] * bl.z;
+            for (int c = 0; c < 6; ++c) acc[c] += y0 * Wb[3 * c] + y1 * Wb[3 * c + 1] + y2 * Wb[3 * c + 2];
+            if (diag) rb += Ya[18 + r];  // ea == eb: rhs  bs(a) -= W_a (Dinv b_l)
         }
     }
-    // fixed reduction tree: lanes (xor shuffles), then warps in order
+    // fixed reduction tree: the 5 slots of a warp (slot order), then the warps in order
+    const int rr0 = lane % 6;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = warp_sum(acc[i]);
+    for (int c = 0; c < 7; ++c) {
+        double v = live ? (c < 6 ? acc[c < 6 ? c : 0] : rb) : 0.0;
+        double s = __shfl_sync(0xffffffffu, v, rr0);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) rb[i] = warp_sum(rb[i]);
-    if (lane == 0) {
+        for (int k = 1; k < 5; ++k) s += __shfl_sync(0xffffffffu, v, rr0 + 6 * k);
+        if (c < 6)
+            acc[c < 6 ? c : 0] = s;
+        else
+            rb = s;
+    }
+    if (lane < 6) {
 #pragma unroll
-        for (int i = 0; i < 36; ++i) red[warp][i] = acc[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) red[warp][36 + i] = rb[i];
+        for (int c = 0; c < 6; ++c) red[warp][6 * lane + c] = acc[c];
+        red[warp][36 + lane] = rb;
     }
     __syncthreads();
     if (threadIdx.x < 42) {
@@ -388,48 +439,71 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(DevWindow w
     // write the 15x15 block of S (upper part of the matrix): S = Hpp + lambda I - scatter(acc)
     const int n = w.n;
     for (int i = threadIdx.x; i < 225; i += kSchurThreads) {
-        const int r = i / 15, c = i - 15 * r;
-        const int gr = 15 * a + r, gc = 15 * b + c;
+        const int rr = i / 15, c = i - 15 * rr;
+        const int gr = 15 * a + rr, gc = 15 * b + c;
         if (gr > gc) continue;
         double v = w.Hpp[(size_t)gr * n + gc];
         if (gr == gc) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
-        const int pr = pose6_index(r), pc = pose6_index(c);
+        const int pr = pose6_index(rr), pc = pose6_index(c);
         if (pr >= 0 && pc >= 0) v -= blockacc[6 * pr + pc];
         w.S[(size_t)gr * n + gc] = v;
     }
     if (diag && threadIdx.x < 15) {
-        const int r = threadIdx.x;
-        double v = w.bp[15 * a + r];
-        const int pr = pose6_index(r);
+        const int rr = threadIdx.x;
+        double v = w.bp[15 * a + rr];
+        const int pr = pose6_index(rr);
         if (pr >= 0) v -= blockacc[36 + pr];
-        w.bs[15 * a + r] = v;
+        w.bs[15 * a + rr] = v;
+    }
+    __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_linearize_v2(cudaStream_t s, const DevWindow& w, int point_ctas) {
-    const int warps = kPointThreads / 32;
-    size_t sm = linearize_v2_smem_bytes(w.K, w.n_free, warps);
-    const size_t imu_sm = sizeof(double) * (216 + 81 + 216 + 9 + 9 + 8);
-    if (sm < imu_sm) sm = imu_sm;
-    static size_t configured = 0;
-    if (sm > configured) {
-        cudaError_t e = cudaFuncSetAttribute(linearize_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        configured = sm;
-    }
-    linearize_v2_kernel<<<point_ctas + w.NI, kPointThreads, sm, s>>>(w, point_ctas);
-    const size_t total = (size_t)w.n * w.n + w.n;
-    int g = (int)((total + 255) / 256);
-    if (g > 592) g = 592;
-    assemble_hpp_kernel<<<g, 256, 0, s>>>(w, point_ctas);
-    return cudaGetLastError();
+size_t linearize_smem_bytes(int K, int n_free) { return linearize_v2_smem_bytes(K, n_free, kPointThreads / 32); }
+
+cudaError_t launch_update_eval_apply(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp);
+cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp);
+cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t configure_point_kernels(const LaunchDims& d);
+cudaError_t configure_chol(const LaunchDims& d);
+
+cudaError_t configure_kernels(const LaunchDims& d) {
+    cudaError_t e = cudaFuncSetAttribute(linearize_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_lin);
+    if (e != cudaSuccess) return e;
+    e = configure_point_kernels(d);
+    if (e != cudaSuccess) return e;
+    return configure_chol(d);
 }
 
-cudaError_t launch_schur_gather(cudaStream_t s, const DevWindow& w) {
-    schur_gather_kernel<<<w.n_pairs, kSchurThreads, 0, s>>>(w);
+cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, const DevWindow* wp,
+                        const LaunchDims& d, cudaEvent_t* probe) {
+    cudaError_t e;
+    if (probe && (e = cudaEventRecord(probe[0], s)) != cudaSuccess) return e;
+    // ---- linearise (skipped on the device unless phase == LINEARIZE): IMU edges beside the mono edges ----
+    if ((e = cudaEventRecord(fork, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
+    linearize_imu_v2_kernel<<<kImuGrid, 32, 0, side>>>(wp);
+    if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
+    linearize_v2_kernel<<<d.point_grid, kPointThreads, d.smem_lin, s>>>(wp);
+    reduce_partials_kernel<<<d.sm_count, 256, 0, s>>>(wp, d.point_grid);
+    if ((e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) return e;
+    assemble_hpp_kernel<<<8 * d.sm_count, 256, 0, s>>>(wp);
+    if (probe && (e = cudaEventRecord(probe[1], s)) != cudaSuccess) return e;
+    if ((e = launch_lm_iter_begin(s, wp)) != cudaSuccess) return e;
+    // ---- one LM trial (skipped unless phase == TRIAL) ----
+    if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
+    schur_prep_kernel<<<d.point_grid, 256, 0, s>>>(wp);
+    schur_gather_kernel<<<2 * d.sm_count, kSchurThreads, 0, s>>>(wp);
+    if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
+    if ((e = launch_chol_cluster(s, wp, d)) != cudaSuccess) return e;
+    if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;
+    if ((e = launch_update_eval_apply(s, wp, d)) != cudaSuccess) return e;
+    if (probe && (e = cudaEventRecord(probe[5], s)) != cudaSuccess) return e;
+    if ((e = launch_lm_decide(s, wp)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 // (g2o/core/sparse_optimizer.cpp:354-419, optimization_algorithm_levenberg.cpp:61-164); all arithmetic
 // runs in the CUDA kernels of lba_kernels.cu / preint.cu.  There is no CPU fallback: without a usable
 // CUDA device vilba_create() returns NULL.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -66,7 +67,7 @@ struct Layout {
     size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, blk_edge_i, blk_edge_j, edge_pt,
         pair_a, pair_b, pair_begin, pair_ea, pair_eb, input_end;
     // work section
-    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, S, Lfac, cdinv, bs, x, lm, dbg, n_culled,
+    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y, S, Lfac, cdinv, bs, x, lm, dbg, n_culled,
         outlier, total;
 };
 
@@ -108,6 +109,8 @@ Layout make_layout(int K, int NI, int P, int E, int n, int n_free, int n_pairs, 
     L.W = take(sizeof(double) * 18 * (size_t)E);
     L.lin_partial = take(sizeof(double) * 27 * (size_t)n_free * lin_ctas);
     L.imu_slot = take(sizeof(double) * 930 * (size_t)NI);
+    L.mono_sum = take(sizeof(double) * 27 * (size_t)n_free);
+    L.Y = take(sizeof(double) * 24 * (size_t)E);
     L.S = take(sizeof(double) * (size_t)n * n);
     L.Lfac = take(sizeof(double) * (size_t)n * n);
     L.cdinv = take(sizeof(double) * (size_t)n);
@@ -126,7 +129,8 @@ Layout make_layout(int K, int NI, int P, int E, int n, int n_free, int n_pairs, 
 struct vilba_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream: IMU-edge linearisation runs beside the mono edges
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr;
     vilba_params prm;
     Arena arena, preint_arena;
     Pinned pinned, pinned_small;
@@ -135,18 +139,19 @@ struct vilba_ctx {
     // resident window
     bool has_window = false;
     Layout L;
-    DevWindow dw;
-    LaunchCfg cfg;
+    DevWindow dw;             // host copy
+    DevWindow* dwp = nullptr; // device copy the kernels read (fixed address => graph-capturable launches)
+    LaunchDims dims;
+    int cap_K = 0, cap_nf = 0, cap_n = 0;  // capacities the shared-memory sizes / the graph were built for
+    cudaGraphExec_t slot_graph = nullptr;
+    bool use_graph = true;   // env VILBA_GRAPH=0 launches the slot kernels one by one
     int win_E = 0, win_NI = 0, win_P = 0, win_K = 0;
+    int last_cur = 0;        // estimate buffer that holds the result of the last solve
     // stats
     vilba_stats stats;
     bool profiling = false;
-    int lin_ctas = 1;
-    bool use_v1 = false;   // env VILBA_V1=1: atomic-based accumulation kernels (kept for A/B)
-    int chol_cluster = 8;  // CTAs in the Cholesky cluster (0 = v1 single-CTA kernel); env VILBA_CHOL_CLUSTER
-    std::vector<cudaEvent_t> prof_events;  // pairs, drained at sync points
-    std::vector<int> prof_kind;
-    size_t prof_used = 0;
+    std::vector<cudaEvent_t> probes;  // 6 events per profiled slot
+    size_t probes_used = 0;
 };
 
 namespace {
@@ -187,36 +192,35 @@ int check_window(const vilba_window* w) {
     return VILBA_OK;
 }
 
-// profiling helpers: an event pair around one launch group, tagged by kind (0 linearize, 1 schur, 2 solve)
-void prof_begin(vilba_ctx* ctx, int kind) {
-    if (!ctx->profiling) return;
-    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
-        for (int i = 0; i < 2; ++i) {
+// profiling: six events per slot (see launch_slot); drained after a stream synchronize
+cudaEvent_t* probe_take(vilba_ctx* ctx) {
+    if (!ctx->profiling) return nullptr;
+    if (ctx->probes_used + 6 > ctx->probes.size()) {
+        for (int i = 0; i < 6; ++i) {
             cudaEvent_t e;
             cudaEventCreate(&e);
-            ctx->prof_events.push_back(e);
-        }
-        ctx->prof_kind.push_back(kind);
-    }
-    ctx->prof_kind[ctx->prof_used / 2] = kind;
-    cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream);
-}
-void prof_end(vilba_ctx* ctx) {
-    if (!ctx->profiling) return;
-    cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream);
-    ctx->prof_used += 2;
-}
-void prof_drain(vilba_ctx* ctx) {  // call after a stream synchronize
-    for (size_t i = 0; i < ctx->prof_used; i += 2) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]) != cudaSuccess) continue;
-        switch (ctx->prof_kind[i / 2]) {
-            case 0: ctx->stats.linearize_ms += ms; ctx->stats.linearize_launches++; break;
-            case 1: ctx->stats.schur_ms += ms; ctx->stats.schur_launches++; break;
-            default: ctx->stats.solve_ms += ms; ctx->stats.solve_launches++; break;
+            ctx->probes.push_back(e);
         }
     }
-    ctx->prof_used = 0;
+    cudaEvent_t* p = &ctx->probes[ctx->probes_used];
+    ctx->probes_used += 6;
+    return p;
+}
+void probe_drain(vilba_ctx* ctx) {
+    for (size_t i = 0; i + 6 <= ctx->probes_used; i += 6) {
+        float lin = 0, sch = 0, chol = 0;
+        cudaEvent_t* p = &ctx->probes[i];
+        if (cudaEventElapsedTime(&lin, p[0], p[1]) != cudaSuccess) continue;
+        cudaEventElapsedTime(&sch, p[2], p[3]);
+        cudaEventElapsedTime(&chol, p[3], p[4]);
+        // a slot whose group returned early (nothing to do in that phase) takes a few microseconds
+        if (lin > 0.008f) ctx->stats.linearize_ms += lin, ctx->stats.linearize_launches++;
+        if (chol > 0.008f) {
+            ctx->stats.schur_ms += sch, ctx->stats.schur_launches++;
+            ctx->stats.solve_ms += chol, ctx->stats.solve_launches++;
+        }
+    }
+    ctx->probes_used = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -283,10 +287,7 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
                 pair_eb[slot] = sw ? ei : ej;
             }
         }
-    const int warps_per_cta_lin = kPointThreads / 32;
-    int lin_ctas = (P + warps_per_cta_lin - 1) / warps_per_cta_lin;
-    if (lin_ctas > 2 * ctx->sm_count) lin_ctas = 2 * ctx->sm_count;
-    if (lin_ctas < 1) lin_ctas = 1;
+    const int lin_ctas = ctx->dims.point_grid;
     const Layout L = make_layout(K, NI, P, E, n, n_free, n_pairs, n_triples, lin_ctas);
     CK(ctx->arena.reserve(L.total), "cudaMalloc(arena)");
     CK(ctx->pinned.reserve(L.input_end), "cudaMallocHost(staging)");
@@ -346,6 +347,8 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     dw.W = reinterpret_cast<double*>(d + L.W);
     dw.lin_partial = reinterpret_cast<double*>(d + L.lin_partial);
     dw.imu_slot = reinterpret_cast<double*>(d + L.imu_slot);
+    dw.mono_sum = reinterpret_cast<double*>(d + L.mono_sum);
+    dw.Y = reinterpret_cast<double*>(d + L.Y);
     dw.blk_edge_i = reinterpret_cast<const int*>(d + L.blk_edge_i);
     dw.blk_edge_j = reinterpret_cast<const int*>(d + L.blk_edge_j);
     dw.edge_pt = reinterpret_cast<const int*>(d + L.edge_pt);
@@ -355,7 +358,6 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     dw.pair_begin = reinterpret_cast<const int*>(d + L.pair_begin);
     dw.pair_ea = reinterpret_cast<const int*>(d + L.pair_ea);
     dw.pair_eb = reinterpret_cast<const int*>(d + L.pair_eb);
-    ctx->lin_ctas = lin_ctas;
     dw.S = reinterpret_cast<double*>(d + L.S);
     dw.Lfac = reinterpret_cast<double*>(d + L.Lfac);
     dw.cdinv = reinterpret_cast<double*>(d + L.cdinv);
@@ -381,13 +383,29 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
 
     ctx->L = L;
     ctx->win_E = E, ctx->win_NI = NI, ctx->win_P = P, ctx->win_K = K;
-    const int warps_per_cta = kPointThreads / 32;
-    int grid = (P + NI + warps_per_cta - 1) / warps_per_cta;
-    const int cap = ctx->sm_count * 8;  // <= 8 resident CTAs of 256 threads per SM
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    ctx->cfg.point_grid = grid;
-    ctx->cfg.sm_count = ctx->sm_count;
+    // shared-memory capacities (and the captured graph) grow monotonically
+    if (K > ctx->cap_K || n_free > ctx->cap_nf || n > ctx->cap_n) {
+        ctx->cap_K = std::max(ctx->cap_K, (K + 31) / 32 * 32);
+        ctx->cap_nf = std::max(ctx->cap_nf, (n_free + 7) / 8 * 8);
+        ctx->cap_n = std::max(ctx->cap_n, 15 * ctx->cap_nf);
+        ctx->dims.smem_point = point_smem_bytes(ctx->cap_K);
+        ctx->dims.smem_lin = linearize_smem_bytes(ctx->cap_K, ctx->cap_nf);
+        ctx->dims.smem_chol = chol_smem_bytes(ctx->cap_n);
+        if (ctx->dims.smem_lin > 227 * 1024 || ctx->dims.smem_chol > 227 * 1024) {
+            ctx->err = "window too large for the shared-memory stages";
+            return VILBA_ERR_ARG;
+        }
+        CK(configure_kernels(ctx->dims), "cudaFuncSetAttribute");
+        if (ctx->slot_graph) {
+            cudaGraphExecDestroy(ctx->slot_graph);
+            ctx->slot_graph = nullptr;
+        }
+    }
+    // device copy of the descriptor (staged behind the inputs in the pinned buffer)
+    CK(ctx->pinned_small.reserve(sizeof(DevWindow) + sizeof(LmState) + 256), "cudaMallocHost(desc)");
+    std::memcpy(ctx->pinned_small.base, &dw, sizeof(DevWindow));
+    CK(cudaMemcpyAsync(ctx->dwp, ctx->pinned_small.base, sizeof(DevWindow), cudaMemcpyHostToDevice, ctx->stream),
+       "H2D descriptor");
     ctx->has_window = true;
     return VILBA_OK;
 }
@@ -413,7 +431,6 @@ int reset_window(vilba_ctx* ctx) {
         CK(cudaMemsetAsync(d + L.obs_chi2, 0, sizeof(double) * (size_t)ctx->win_E, s), "reset chi2");
     }
     CK(cudaMemsetAsync(d + L.lm, 0, sizeof(LmState), s), "reset lm");
-    CK(cudaMemsetAsync(d + L.n_culled, 0, sizeof(int) * 4, s), "reset counters");
     if (std::getenv("VILBA_DEBUG_COUNTERS")) {
         long long h[16];
         if (cudaMemcpy(h, d + L.dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[8] > 0) {
@@ -426,80 +443,82 @@ int reset_window(vilba_ctx* ctx) {
     return VILBA_OK;
 }
 
-int read_lm(vilba_ctx* ctx, LmState* out) {
-    CK(ctx->pinned_small.reserve(sizeof(LmState) + 64), "cudaMallocHost(lm)");
-    CK(cudaMemcpyAsync(ctx->pinned_small.base, ctx->dw.lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream),
-       "D2H lm");
+// D2H of the controller state; waits for the stream while polling the caller's stop flag
+int read_lm(vilba_ctx* ctx, LmState* out, const volatile uint8_t* stop_flag) {
+    char* hp = ctx->pinned_small.base + sizeof(DevWindow) + 64;
+    CK(cudaMemcpyAsync(hp, ctx->dw.lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream), "D2H lm");
+    if (stop_flag) {
+        bool sent = false;
+        while (cudaStreamQuery(ctx->stream) == cudaErrorNotReady) {
+            if (!sent && *stop_flag) {  // mirror of `bool* pbStopFlag` (sparse_optimizer.h:188)
+                static const int one = 1;
+                cudaMemcpyAsync(&ctx->dw.lm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream2);
+                sent = true;
+            }
+        }
+    }
     CK(cudaStreamSynchronize(ctx->stream), "sync");
-    std::memcpy(out, ctx->pinned_small.base, sizeof(LmState));
-    prof_drain(ctx);
+    std::memcpy(out, hp, sizeof(LmState));
+    probe_drain(ctx);
     return VILBA_OK;
 }
 
 bool stop_requested(const volatile uint8_t* f) { return f && *f; }
 
-// SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg (sparse_optimizer.cpp:354-419)
-int run_stage(vilba_ctx* ctx, int stage, int iterations, int n_active, vilba_result* out,
-              const volatile uint8_t* stop_flag) {
-    const DevWindow& dw = ctx->dw;
+int ensure_graph(vilba_ctx* ctx) {
+    if (!ctx->use_graph || ctx->slot_graph) return VILBA_OK;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
+    cudaError_t e = launch_slot(ctx->stream, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, nullptr);
+    cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &g);
+    if (fail(ctx, e, "capture slot") || fail(ctx, e2, "end capture")) return VILBA_ERR_CUDA;
+    e = cudaGraphInstantiate(&ctx->slot_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (fail(ctx, e, "graph instantiate")) return VILBA_ERR_CUDA;
+    return VILBA_OK;
+}
+
+// SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg (sparse_optimizer.cpp:354-419).
+// The loop itself runs on the device: the host enqueues slots (CUDA graph launches) without
+// synchronising and looks at the controller state once they have drained.
+int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, const volatile uint8_t* stop_flag,
+              LmState* lm) {
     cudaStream_t s = ctx->stream;
     vilba_stats& stt = ctx->stats;
     // computeActiveErrors + activeRobustChi2 at the first iteration; later iterations inherit currentChi
     // of the accepted trial (identical by construction: the errors are those of the accepted state)
-    CK(launch_update_eval(s, dw, ctx->cfg, false), "eval");
-    CK(launch_lm_stage_begin(s, dw), "lm_stage_begin");
+    CK(launch_eval_initial(s, ctx->dwp, ctx->dims), "eval");
+    CK(launch_stage_begin(s, ctx->dwp, stage, iterations), "stage_begin");
     stt.kernel_launches += 2;
-    bool ok = true;
-    for (int it = 0; it < iterations && !stop_requested(stop_flag) && ok; ++it) {
-        prof_begin(ctx, 0);
-        if (ctx->use_v1)
-            CK(launch_linearize(s, dw, ctx->cfg), "linearize");
-        else
-            CK(launch_linearize_v2(s, dw, ctx->lin_ctas), "linearize_v2");
-        prof_end(ctx);
-        CK(launch_lm_iter_begin(s, dw, it), "lm_iter_begin");
-        stt.kernel_launches += 2 + (dw.NI > 0 ? 1 : 0);
-        stt.edges_linearized += n_active;
-        LmState lm;
-        do {
-            prof_begin(ctx, 1);
-            if (ctx->use_v1)
-                CK(launch_schur(s, dw, ctx->cfg), "schur");
+    const bool graph = ctx->use_graph && !ctx->profiling;
+    if (graph) {
+        int r = ensure_graph(ctx);
+        if (r != VILBA_OK) return r;
+    }
+    const int first_trace = lm->n_trace;
+    int slots = iterations + 1;  // one trial per iteration when every step is accepted, plus one spare
+    for (int round = 0; round < 64; ++round) {
+        for (int i = 0; i < slots; ++i) {
+            if (graph)
+                CK(cudaGraphLaunch(ctx->slot_graph, s), "graph launch");
             else
-                CK(launch_schur_gather(s, dw), "schur_gather");
-            prof_end(ctx);
-            prof_begin(ctx, 2);
-            if (ctx->chol_cluster > 0)
-                CK(launch_chol_cluster(s, dw, ctx->chol_cluster), "chol_cluster");
-            else
-                CK(launch_chol_solve(s, dw), "chol");
-            prof_end(ctx);
-            CK(launch_update_eval(s, dw, ctx->cfg, true), "update_eval");
-            if (stop_requested(stop_flag)) {
-                const int one = 1;
-                CK(cudaMemcpyAsync(&dw.lm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, s), "stop");
-            }
-            CK(launch_lm_decide(s, dw), "lm_decide");
-            stt.kernel_launches += 5;
-            stt.lm_trials++;
-            int r = read_lm(ctx, &lm);
-            if (r != VILBA_OK) return r;
-        } while (lm.iter_result == -1);
-        stt.lm_iterations++;
-        if (out->n_trace < VILBA_MAX_TRACE) {
-            vilba_iter_record& rec = out->trace[out->n_trace++];
-            rec.stage = stage;
-            rec.iteration = it;
-            rec.trials = lm.qmax;
-            rec.result = lm.iter_result;
-            rec.n_active_edges = n_active;
-            rec.accepted = lm.accepted;
-            rec.chi2_initial = lm.ini_chi;
-            rec.chi2_final = lm.current_chi;
-            rec.lambda = lm.lambda;
-            rec.lambda_first_trial = lm.lambda_first;
+                CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, probe_take(ctx)), "slot");
+            stt.kernel_launches += kKernelsPerSlot;
         }
-        ok = (lm.iter_result == 0);
+        int r = read_lm(ctx, lm, stop_flag);
+        if (r != VILBA_OK) return r;
+        if (lm->phase == PH_DONE) break;
+        slots = 2;  // rejected trials used up the slack: keep going
+    }
+    for (int i = first_trace; i < lm->n_trace && out->n_trace < VILBA_MAX_TRACE; ++i) {
+        const IterRec& t = lm->trace[i];
+        vilba_iter_record& rec = out->trace[out->n_trace++];
+        rec.stage = t.stage, rec.iteration = t.iteration, rec.trials = t.trials, rec.result = t.result;
+        rec.n_active_edges = t.n_active, rec.accepted = t.accepted;
+        rec.chi2_initial = t.chi0, rec.chi2_final = t.chi1, rec.lambda = t.lambda, rec.lambda_first_trial = t.lambda_first;
+        stt.lm_iterations++;
+        stt.lm_trials += t.trials;
+        stt.edges_linearized += t.n_active;
     }
     return VILBA_OK;
 }
@@ -519,47 +538,40 @@ int solve_resident(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* st
         return VILBA_ABORTED;
     }
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    const DevWindow& dw = ctx->dw;
     cudaStream_t s = ctx->stream;
     int r = reset_window(ctx);
     if (r != VILBA_OK) return r;
     CK(cudaEventRecord(ctx->ev_a, s), "event");
-    CK(launch_imu_prepare(s, dw), "imu_prepare");
-    ctx->stats.kernel_launches += dw.NI > 0 ? 1 : 0;
-    const int n_all = dw.E + 2 * dw.NI;
-    r = run_stage(ctx, 1, ctx->prm.iters_stage1, n_all, out, stop_flag);
+    CK(launch_imu_prepare(s, ctx->dwp), "imu_prepare");
+    ctx->stats.kernel_launches += 1;
+    LmState lm;
+    std::memset(&lm, 0, sizeof(lm));
+    r = run_stage(ctx, 1, ctx->prm.iters_stage1, out, stop_flag, &lm);
     if (r != VILBA_OK) return r;
-    if (!stop_requested(stop_flag)) {  // bDoMore (Optimizer.cpp:2650-2656)
-        int* n_culled_dev = reinterpret_cast<int*>(ctx->arena.base + ctx->L.n_culled);
-        CK(launch_cull(s, dw, ctx->cfg, n_culled_dev), "cull");
+    if (!stop_requested(stop_flag) && !lm.stop) {  // bDoMore (Optimizer.cpp:2650-2656)
+        CK(launch_cull(s, ctx->dwp, ctx->dims), "cull");
         ctx->stats.kernel_launches += 1;
-        CK(ctx->pinned_small.reserve(sizeof(LmState) + 64), "cudaMallocHost");
-        CK(cudaMemcpyAsync(ctx->pinned_small.base, n_culled_dev, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H");
-        CK(cudaStreamSynchronize(s), "sync");
-        int n_culled = 0;
-        std::memcpy(&n_culled, ctx->pinned_small.base, sizeof(int));
-        out->n_outliers_stage1 = n_culled;
-        r = run_stage(ctx, 2, ctx->prm.iters_stage2, n_all - n_culled, out, stop_flag);
+        r = run_stage(ctx, 2, ctx->prm.iters_stage2, out, stop_flag, &lm);
         if (r != VILBA_OK) return r;
+        out->n_outliers_stage1 = lm.n_culled;
         out->stage2_ran = 1;
     }
     uint8_t* outl = reinterpret_cast<uint8_t*>(ctx->arena.base + ctx->L.outlier);
-    CK(launch_final_flags(s, dw, ctx->cfg, outl), "final_flags");
+    CK(launch_final_flags(s, ctx->dwp, ctx->dims, outl), "final_flags");
     ctx->stats.kernel_launches += 1;
     CK(cudaEventRecord(ctx->ev_b, s), "event");
     CK(cudaStreamSynchronize(s), "sync");
-    prof_drain(ctx);
+    probe_drain(ctx);
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b), "elapsed");
     out->solve_ms = ms;
+    ctx->last_cur = lm.cur;
     return VILBA_OK;
 }
 
 int download_window(vilba_ctx* ctx, vilba_result* out) {
     if (!ctx->has_window) return VILBA_ERR_ARG;
-    LmState lm;
-    int r = read_lm(ctx, &lm);
-    if (r != VILBA_OK) return r;
+    struct { int cur; } lm = {ctx->last_cur};
     const Layout& L = ctx->L;
     char* d = ctx->arena.base;
     cudaStream_t s = ctx->stream;
@@ -623,9 +635,20 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::atoi(e);
-    if (const char* e = std::getenv("VILBA_V1")) ctx->use_v1 = std::atoi(e) != 0;
+    ctx->dims.sm_count = ctx->sm_count;
+    ctx->dims.point_grid = kPointGridPerSM * ctx->sm_count;
+    ctx->dims.chol_cluster = 8;
+    ctx->dims.smem_point = ctx->dims.smem_lin = ctx->dims.smem_chol = 0;
+    if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->dims.chol_cluster = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
+    if (cudaMalloc(&ctx->dwp, sizeof(DevWindow)) != cudaSuccess) {
+        delete ctx;
+        return nullptr;
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
         std::fprintf(stderr, "vilba_create: %s\n", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -638,13 +661,18 @@ void vilba_destroy(vilba_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->probes) cudaEventDestroy(e);
+    if (ctx->slot_graph) cudaGraphExecDestroy(ctx->slot_graph);
+    if (ctx->dwp) cudaFree(ctx->dwp);
     ctx->arena.release();
     ctx->preint_arena.release();
     ctx->pinned.release();
     ctx->pinned_small.release();
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
