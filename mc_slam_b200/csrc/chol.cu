@@ -107,6 +107,82 @@ __device__ __forceinline__ bool warp_ldlt16_mb4(double (&a)[NB], int lane, doubl
     return ok;
 }
 
+// Lower-triangular 4x4 tiles enumerated column by column: t = off(tj) + (ti - tj), off(tj) = tj (2 trp - tj + 1) / 2,
+// so that consecutive threads own consecutive tile ROWS of one tile column (coalesced global access).
+__device__ __forceinline__ void decode_tile(int t, int trp, int& ti, int& tj) {
+    const float bq = 2.0f * (float)trp + 1.0f;
+    int j = (int)((bq - sqrtf(fmaxf(bq * bq - 8.0f * (float)t, 0.0f))) * 0.5f);
+    j = max(0, min(j, trp - 1));
+    while (j > 0 && j * (2 * trp - j + 1) / 2 > t) --j;
+    while (j + 1 < trp && (j + 1) * (2 * trp - j) / 2 <= t) ++j;
+    tj = j;
+    ti = j + (t - j * (2 * trp - j + 1) / 2);
+}
+
+// Back substitution L^T x = y: the unknowns live in the registers of ONE warp (lane owns c = lane + 32 i);
+// per unknown the serial chain is one multiply, one shuffle and one fma.  The 32 rows of L that a
+// block of 32 unknowns needs are staged in shared memory by the other warps (double buffered, coalesced
+// reads of the row-major factor) so the chain never waits for L2.
+template <int SLOTS>
+__device__ __forceinline__ void backsub_staged(const double* __restrict__ Lr, int ld, const double* __restrict__ rdiag,
+                                               const double* __restrict__ yf, double* __restrict__ xout, int n,
+                                               double* stage /* 2 x 16 x (32*SLOTS+1) */, int tid, int nt) {
+    constexpr int LDB = 32 * SLOTS + 1;
+    constexpr int HB = 16;  // rows per staged half-block
+    const int lane = tid & 31;
+    const int nslots = (n + 31) / 32;
+    const int nhalf = 2 * nslots;  // half-blocks, processed from the last one down
+    auto load_half = [&](int h, double* buf, int t0, int tn) {
+        const int ncols = 32 * (h / 2 + 1);
+        for (int i = t0; i < HB * ncols; i += tn) {
+            const int r = i / ncols, c = i - r * ncols;
+            const int j = HB * h + r;
+            buf[r * LDB + c] = (j < n && c < j) ? Lr[(size_t)j * ld + c] : 0.0;
+        }
+    };
+    load_half(nhalf - 1, stage, tid, nt);
+    __syncthreads();
+    double yv[SLOTS];
+    if (tid < 32) {
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) yv[i] = (lane + 32 * i < n) ? yf[lane + 32 * i] : 0.0;
+    }
+#pragma unroll
+    for (int slot = SLOTS - 1; slot >= 0; --slot) {
+        if (slot >= nslots) continue;
+        const double rd = (tid < 32 && lane + 32 * slot < n) ? rdiag[lane + 32 * slot] : 0.0;
+#pragma unroll
+        for (int hh = 1; hh >= 0; --hh) {
+            const int h = 2 * slot + hh;
+            double* buf = stage + ((nhalf - 1 - h) & 1) * HB * LDB;
+            double* nxt = stage + ((nhalf - h) & 1) * HB * LDB;
+            if (tid >= 32) {
+                if (h > 0) load_half(h - 1, nxt, tid - 32, nt - 32);
+            } else {
+#pragma unroll 4
+                for (int r = HB - 1; r >= 0; --r) {
+                    const int jj = HB * hh + r;
+                    const double* row = buf + r * LDB;
+                    double lv[SLOTS];
+#pragma unroll
+                    for (int i = 0; i < SLOTS; ++i) lv[i] = (i <= slot) ? row[lane + 32 * i] : 0.0;  // 0 for c >= j
+                    const double xj = __shfl_sync(0xffffffffu, yv[slot] * rd, jj);
+                    if (lane == jj) yv[slot] = xj;
+#pragma unroll
+                    for (int i = 0; i < SLOTS; ++i)
+                        if (i <= slot) yv[i] -= lv[i] * xj;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < 32) {
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i)
+            if (lane + 32 * i < n) xout[lane + 32 * i] = yv[i];
+    }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWindow* __restrict__ wp) {
@@ -117,12 +193,14 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
     const int csize = (int)cluster.num_blocks();
     extern __shared__ double smem[];
     const int n = w.n;
+    const int ld = w.lds;  // leading dimension of S / Lfac (n rounded up to a multiple of 4: aligned 16-byte row groups)
     double* Dt = smem;                        // NB x NB   unit-lower L11, transposed: Dt[k*NB + c] = l(c,k)
     double* Pn = Dt + NB * NB;                // (n + 8) x LDP  panel X = A21 L11^-T D^-1/2 (+ rhs row + zero pad)
     double* xs = Pn + (size_t)(n + 8) * LDP;  // n   solution during back substitution
     double* Dsq = xs + n;                     // NB  sqrt(d)
     double* Dis = Dsq + NB;                   // NB  1/sqrt(d)
     double* Wsm = Dis + NB;                   // 80  warp-private scratch of the diagonal factorisation
+    double* Stage = Wsm + 80;                 // 2 x 16 x 321  row stage of the back substitution (n <= 320)
     double* A = w.S;       // working matrix: column block k is only READ in step k, the trailing part is updated
     double* Lf = w.Lfac;   // factor output (same addressing); written by CTA 0, never read inside the loop
     double* y = w.bs;      // rhs row, updated like a matrix row
@@ -162,11 +240,15 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 double v = (c == lane) ? 1.0 : 0.0;
-                if (lane < jb && c <= lane) v = A[(size_t)(j0 + c) * n + j0 + lane];
+                if (lane < jb && c <= lane) v = A[(size_t)(j0 + c) * ld + j0 + lane];
                 drow[c] = v;
             }
             TPH(0)
+#ifdef VILBA_CHOL_TIMING
+            const bool ok = (w.dbg_flags & 4) ? true : warp_ldlt16_mb4(drow, lane, Wsm);
+#else
             const bool ok = warp_ldlt16_mb4(drow, lane, Wsm);
+#endif
             if (!ok && lane == 0) s_fail = 1;
             double dr = 1.0;
 #pragma unroll
@@ -183,7 +265,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
             if (crank == 0 && lane < jb) {  // Cholesky factor block: L(r,c) = l(r,c) sqrt(d_c), L(r,r) = sqrt(d_r)
 #pragma unroll
                 for (int c = 0; c < NB; ++c)
-                    if (c <= lane) Lf[(size_t)(j0 + c) * n + j0 + lane] = (c == lane) ? sq : drow[c] * Dsq[c];
+                    if (c <= lane) Lf[(size_t)(j0 + lane) * ld + j0 + c] = (c == lane) ? sq : drow[c] * Dsq[c];
                 rdiag[j0 + lane] = isq;
             }
             TPH(1)
@@ -195,25 +277,30 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                 const int gi = j0 + jb + rr;
 #pragma unroll
                 for (int c = 0; c < NB; ++c)
-                    xr0[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * n + gi]) : 0.0;
+                    xr0[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * ld + gi]) : 0.0;
             }
             if (t_first < ntiles) {
-                // triangular decode: t = ti (ti + 1) / 2 + tj
-                int ti = (int)((sqrtf(8.0f * (float)t_first + 1.0f) - 1.0f) * 0.5f);
-                while (ti * (ti + 1) / 2 > t_first) --ti;
-                while ((ti + 1) * (ti + 2) / 2 <= t_first) ++ti;
-                ti0 = ti;
-                tj0 = t_first - ti * (ti + 1) / 2;
+                decode_tile(t_first, trp, ti0, tj0);
+                if (ti0 > tj0 && 4 * ti0 + 3 < rows_below) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const int r = 4 * ti0 + a, c = 4 * tj0 + b;
-                        double v = 0.0;
-                        if (r < m_rows && c < rows_below && c <= r)
-                            v = (r == rows_below) ? y[j0 + jb + c] : A[(size_t)(j0 + jb + c) * n + (j0 + jb + r)];
-                        old[a][b] = v;
+                    for (int b = 0; b < 4; ++b) {
+                        const double2* p = reinterpret_cast<const double2*>(
+                            &A[(size_t)(j0 + jb + 4 * tj0 + b) * ld + (j0 + jb + 4 * ti0)]);
+                        const double2 lo = p[0], hi = p[1];
+                        old[0][b] = lo.x, old[1][b] = lo.y, old[2][b] = hi.x, old[3][b] = hi.y;
                     }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const int r = 4 * ti0 + a, c = 4 * tj0 + b;
+                            double v = 0.0;
+                            if (r < m_rows && c < rows_below && c <= r)
+                                v = (r == rows_below) ? y[j0 + jb + c] : A[(size_t)(j0 + jb + c) * ld + (j0 + jb + r)];
+                            old[a][b] = v;
+                        }
+                }
             }
         }
         __syncthreads();
@@ -233,8 +320,11 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                 } else {
 #pragma unroll
                     for (int c = 0; c < NB; ++c)
-                        xr[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * n + gi]) : 0.0;
+                        xr[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * ld + gi]) : 0.0;
                 }
+#ifdef VILBA_CHOL_TIMING
+                if (!(w.dbg_flags & 2))
+#endif
 #pragma unroll
                 for (int k = 0; k < NB - 1; ++k) {
 #pragma unroll
@@ -253,7 +343,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                             if (is_rhs)
                                 yf[j0 + c] = xr[c];
                             else
-                                Lf[(size_t)(j0 + c) * n + gi] = xr[c];
+                                Lf[(size_t)gi * ld + j0 + c] = xr[c];
                         }
                 }
             }
@@ -262,16 +352,17 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
         __syncthreads();
         TPH(4)
         // ---- (5) trailing update A22 -= X X^T (and rhs -= x_rhs X^T), lower tiles split over the cluster ----
+#ifdef VILBA_CHOL_TIMING
+        if (!is_factor_warp && !(w.dbg_flags & 1)) {
+#else
         if (!is_factor_warp) {
+#endif
             for (int t = t_first; t < ntiles; t += gthreads) {
                 int ti, tj;
                 if (t == t_first) {
                     ti = ti0, tj = tj0;
                 } else {
-                    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-                    while (ti * (ti + 1) / 2 > t) --ti;
-                    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-                    tj = t - ti * (ti + 1) / 2;
+                    decode_tile(t, trp, ti, tj);
                 }
                 double acc[4][4];
 #pragma unroll
@@ -291,21 +382,45 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                     acc[3][0] += vr3 * vc0, acc[3][1] += vr3 * vc1, acc[3][2] += vr3 * vc2, acc[3][3] += vr3 * vc3;
                 }
                 const bool pre = (t == t_first);
+                if (ti > tj && 4 * ti + 3 < rows_below) {
+                    // interior tile: the 4 rows of a column are 32 contiguous, 16-byte aligned bytes
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const int r = 4 * ti + a, c = 4 * tj + b;
-                        if (r >= m_rows || c >= rows_below || c > r) continue;
-                        double* p =
-                            (r == rows_below) ? &y[j0 + jb + c] : &A[(size_t)(j0 + jb + c) * n + (j0 + jb + r)];
-                        const double o = pre ? old[a][b] : *p;
-                        *p = o - acc[a][b];
+                    for (int b = 0; b < 4; ++b) {
+                        double2* p = reinterpret_cast<double2*>(&A[(size_t)(j0 + jb + 4 * tj + b) * ld + (j0 + jb + 4 * ti)]);
+                        double2 lo, hi;
+                        if (pre) {
+                            lo = make_double2(old[0][b], old[1][b]);
+                            hi = make_double2(old[2][b], old[3][b]);
+                        } else {
+                            lo = p[0];
+                            hi = p[1];
+                        }
+                        lo.x -= acc[0][b], lo.y -= acc[1][b], hi.x -= acc[2][b], hi.y -= acc[3][b];
+                        p[0] = lo;
+                        p[1] = hi;
                     }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const int r = 4 * ti + a, c = 4 * tj + b;
+                            if (r >= m_rows || c >= rows_below || c > r) continue;
+                            double* p =
+                                (r == rows_below) ? &y[j0 + jb + c] : &A[(size_t)(j0 + jb + c) * ld + (j0 + jb + r)];
+                            const double o = pre ? old[a][b] : *p;
+                            *p = o - acc[a][b];
+                        }
+                }
             }
         }
         TPH(5)
         // ---- (6) publish the updated trailing matrix to the whole cluster ----
+#ifdef VILBA_CHOL_TIMING
+        if (w.dbg_flags & 8)
+            __syncthreads();
+        else
+#endif
         if (csize > 1)
             cluster.sync();
         else
@@ -315,62 +430,32 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
 
     // ---- back substitution L^T x = y on CTA 0 ----
     if (crank != 0) return;
+#ifdef VILBA_CHOL_TIMING
+    if (w.dbg_flags & 16) return;
+#endif
     __syncthreads();  // CTA 0's own writes to yf / Lf / rdiag are ordered by the block barrier
-    for (int i = tid; i < n; i += nt) xs[i] = yf[i];
-    const int nblk = (n + NB - 1) / NB;
-    double lcol[NB];   // warp 0: lane c holds column c of the diagonal block, L(j0+j, j0+c), j >= c
-    double lrow[NB];   // all threads: thread c holds L(j0+t, c), t = 0..15, for its column c < j0
-    double rd = 0.0;
-    auto prefetch = [&](int kb) {
-        const int j0 = kb * NB;
-        const int jb = min(NB, n - j0);
+    double* stage = Pn;  // the panel area is free now
+    if (n <= 160 && w.chol_stage) {
+        backsub_staged<5>(Lf, ld, rdiag, yf, xs, n, Stage, tid, nt);
+    } else if (n <= 320 && w.chol_stage) {
+        backsub_staged<10>(Lf, ld, rdiag, yf, xs, n, Stage, tid, nt);
+    } else {
+        // large systems: the unknowns live in shared memory (same algorithm, one row per step, one warp)
         if (tid < 32) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-                lcol[j] = (lane < jb && j < jb && j >= lane) ? Lf[(size_t)(j0 + lane) * n + j0 + j] : 0.0;
-            rd = (lane < jb) ? rdiag[j0 + lane] : 0.0;
-        }
-        if (tid < j0) {
-            const double* col = Lf + (size_t)tid * n + j0;
-#pragma unroll
-            for (int t = 0; t < NB; ++t) lrow[t] = (t < jb) ? col[t] : 0.0;
-        }
-    };
-    prefetch(nblk - 1);
-    __syncthreads();
-    for (int kb = nblk - 1; kb >= 0; --kb) {
-        const int j0 = kb * NB;
-        const int jb = min(NB, n - j0);
-        if (tid < 32) {
-            double yv = (lane < jb) ? xs[j0 + lane] : 0.0;
-#pragma unroll
-            for (int j = NB - 1; j >= 0; --j) {
-                // x_j = y_j / L(j,j) in lane j, broadcast, then y_c -= L(j,c) x_j for c < j
-                const double xj = __shfl_sync(0xffffffffu, yv * rd, j);
-                if (lane == j) yv = xj;
-                if (lane < j) yv -= lcol[j] * xj;
+            for (int i = lane; i < n; i += 32) xs[i] = yf[i];
+            __syncwarp();
+            for (int j = n - 1; j >= 0; --j) {
+                const double xj = xs[j] * rdiag[j];
+                __syncwarp();
+                if (lane == 0) xs[j] = xj;
+                const double* row = Lf + (size_t)j * ld;
+                for (int c = lane; c < j; c += 32) xs[c] -= row[c] * xj;
+                __syncwarp();
             }
-            if (lane < jb) xs[j0 + lane] = yv;
         }
-        __syncthreads();
-        // y_c -= sum_t L(j0+t, c) x(j0+t) for c < j0, with the block row prefetched one step ahead
-        double s = 0.0;
-        if (tid < j0) {
-#pragma unroll
-            for (int t = 0; t < NB; ++t) s += lrow[t] * xs[j0 + t];
-        }
-        for (int c = tid + nt; c < j0; c += nt) {  // n > blockDim: remaining columns without prefetch
-            const double* col = Lf + (size_t)c * n + j0;
-            double s2 = 0.0;
-#pragma unroll
-            for (int t = 0; t < NB; ++t)
-                if (t < jb) s2 += col[t] * xs[j0 + t];
-            xs[c] -= s2;
-        }
-        if (kb > 0) prefetch(kb - 1);
-        if (tid < j0) xs[tid] -= s;
-        __syncthreads();
     }
+    (void)stage;
+    __syncthreads();
     for (int i = tid; i < n; i += nt) w.x[i] = xs[i];
     if (tid == 0) w.lm->chol_fail = s_fail;
 #ifdef VILBA_CHOL_TIMING
@@ -382,8 +467,11 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
 #endif
 }
 
+bool chol_has_stage(int n_cap) { return n_cap <= 640; }
+
 size_t chol_smem_bytes(int n) {
-    return sizeof(double) * ((size_t)NB * NB + (size_t)(n + 8) * LDP + (size_t)n + 2 * NB + 80);
+    const size_t stage = chol_has_stage(n) ? (size_t)2 * 16 * 321 : 0;
+    return sizeof(double) * ((size_t)NB * NB + (size_t)(n + 8) * LDP + (size_t)n + 2 * NB + 80 + stage);
 }
 
 cudaError_t configure_chol(const LaunchDims& d) {

@@ -63,6 +63,7 @@ struct LmState {
 
 struct DevWindow {
     int K, NI, P, E, n_free, n;  // n = 15 * n_free
+    int lds;                     // leading dimension of S and Lfac: n rounded up to a multiple of 4
     // estimates, double buffered (index LmState::cur = accepted state, 1-cur = trial state)
     double* kf_state[2];  // K * 22
     double* pts[2];       // P * 3
@@ -85,6 +86,7 @@ struct DevWindow {
     double* W;    // E * 18  H_pl block of the edge, 6x3 rows [P,Phi]
     double* S;    // n * n   reduced camera system (upper triangle used)
     double* Lfac; // n * n   Cholesky factor of S (same addressing as S)
+    double* cminv; // (n/16 + 2) * 256   inverse of every 16x16 diagonal factor block (look-ahead variant)
     double* cdinv; // n      1 / L(j,j)
     double* bs;   // n
     double* x;    // n       pose increment
@@ -104,6 +106,8 @@ struct DevWindow {
     const int* pair_eb;
     LmState* lm;
     long long* dbg;  // optional debug counters (16 x int64), may be null
+    int dbg_flags;   // timing-ablation switches (only honoured by -DVILBA_CHOL_TIMING builds)
+    int chol_stage;  // 1 if the Cholesky launch carries the shared-memory row stage of the back substitution
     // calibration (g2otypes.h:686-705)
     double fx, fy, cx, cy;
     double Rcb[9];  // Rbc^T
@@ -136,6 +140,7 @@ struct LaunchDims {
 size_t point_smem_bytes(int K);
 size_t linearize_smem_bytes(int K, int n_free);
 size_t chol_smem_bytes(int n);
+bool chol_has_stage(int n_cap);
 cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels
 
 cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp);

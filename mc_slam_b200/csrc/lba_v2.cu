@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWi
         if (gr == gc) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
         const int pr = pose6_index(rr), pc = pose6_index(c);
         if (pr >= 0 && pc >= 0) v -= blockacc[6 * pr + pc];
-        w.S[(size_t)gr * n + gc] = v;
+        w.S[(size_t)gr * w.lds + gc] = v;
     }
     if (diag && threadIdx.x < 15) {
         const int rr = threadIdx.x;

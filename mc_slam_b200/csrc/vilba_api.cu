@@ -67,7 +67,7 @@ struct Layout {
     size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, blk_edge_i, blk_edge_j, edge_pt,
         pair_a, pair_b, pair_begin, pair_ea, pair_eb, input_end;
     // work section
-    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y, S, Lfac, cdinv, bs, x, lm, dbg, n_culled,
+    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y, S, Lfac, cminv, cdinv, bs, x, lm, dbg, n_culled,
         outlier, total;
 };
 
@@ -111,8 +111,10 @@ Layout make_layout(int K, int NI, int P, int E, int n, int n_free, int n_pairs, 
     L.imu_slot = take(sizeof(double) * 930 * (size_t)NI);
     L.mono_sum = take(sizeof(double) * 27 * (size_t)n_free);
     L.Y = take(sizeof(double) * 24 * (size_t)E);
-    L.S = take(sizeof(double) * (size_t)n * n);
-    L.Lfac = take(sizeof(double) * (size_t)n * n);
+    const size_t lds = ((size_t)n + 3) & ~(size_t)3;
+    L.S = take(sizeof(double) * lds * n);
+    L.Lfac = take(sizeof(double) * lds * n);
+    L.cminv = take(sizeof(double) * 256 * ((size_t)n / 16 + 2));
     L.cdinv = take(sizeof(double) * (size_t)n);
     L.bs = take(sizeof(double) * (size_t)n);
     L.x = take(sizeof(double) * (size_t)n);
@@ -327,6 +329,7 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     DevWindow& dw = ctx->dw;
     std::memset(&dw, 0, sizeof(dw));
     dw.K = K, dw.NI = NI, dw.P = P, dw.E = E, dw.n_free = n_free, dw.n = n;
+    dw.lds = (n + 3) & ~3;
     for (int b = 0; b < 2; ++b) {
         dw.kf_state[b] = reinterpret_cast<double*>(d + L.kf_state[b]);
         dw.pts[b] = reinterpret_cast<double*>(d + L.pts[b]);
@@ -360,11 +363,13 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     dw.pair_eb = reinterpret_cast<const int*>(d + L.pair_eb);
     dw.S = reinterpret_cast<double*>(d + L.S);
     dw.Lfac = reinterpret_cast<double*>(d + L.Lfac);
+    dw.cminv = reinterpret_cast<double*>(d + L.cminv);
     dw.cdinv = reinterpret_cast<double*>(d + L.cdinv);
     dw.bs = reinterpret_cast<double*>(d + L.bs);
     dw.x = reinterpret_cast<double*>(d + L.x);
     dw.lm = reinterpret_cast<LmState*>(d + L.lm);
     dw.dbg = reinterpret_cast<long long*>(d + L.dbg);
+    if (const char* e = std::getenv("VILBA_CHOL_ABLATE")) dw.dbg_flags = std::atoi(e);
     dw.fx = w->fx, dw.fy = w->fy, dw.cx = w->cx, dw.cy = w->cy;
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) dw.Rcb[3 * r + c] = w->Rbc[3 * c + r];  // Rcb = Rbc^T
@@ -401,6 +406,7 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
             ctx->slot_graph = nullptr;
         }
     }
+    dw.chol_stage = chol_has_stage(ctx->cap_n) ? 1 : 0;
     // device copy of the descriptor (staged behind the inputs in the pinned buffer)
     CK(ctx->pinned_small.reserve(sizeof(DevWindow) + sizeof(LmState) + 256), "cudaMallocHost(desc)");
     std::memcpy(ctx->pinned_small.base, &dw, sizeof(DevWindow));

@@ -167,7 +167,36 @@ __global__ void k_ldlt(const double* blk, double* out, long long* cyc) {
     out[lane] = acc;
     if (lane == 0) cyc[0] = t1 - t0;
 }
+__global__ void k_dfma_tput(double* out, long long* cyc, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = out[threadIdx.x] + i;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 128; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    out[threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[0] = (t1 - t0);
+}
 int main() {
+    {
+        double* o; long long* cy; cudaMalloc(&o, 1024 * 8); cudaMemset(o, 0, 8192); cudaMallocManaged(&cy, 64);
+        for (int nt : {32, 128, 256, 512, 1024}) {
+            k_dfma_tput<<<1, nt>>>(o, cy, 1.0000001, 1e-9); cudaDeviceSynchronize();
+            double fmas = (double)nt * 128 * 32;  // thread-level FMAs
+            printf("DFMA throughput, %4d threads/SM: %.1f FMA/clk/SM\n", nt, fmas / (double)cy[0]);
+        }
+    }
     {
         double h[256];
         for (int r = 0; r < 16; ++r) for (int c = 0; c < 16; ++c) h[r * 16 + c] = (r == c) ? 20.0 + r : 1.0 / (1 + r + c);
