@@ -232,8 +232,6 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
         const int gthreads = csize * nwt;
         const int t_first = crank * nwt + wt;
         double xr0[NB];
-        double old[4][4];
-        int ti0 = 0, tj0 = 0;
         if (is_factor_warp) {
             // ---- factor warp: (1) load the diagonal block (identity padded), (3) factor, publish ----
             double drow[NB];
@@ -279,29 +277,6 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                 for (int c = 0; c < NB; ++c)
                     xr0[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * ld + gi]) : 0.0;
             }
-            if (t_first < ntiles) {
-                decode_tile(t_first, trp, ti0, tj0);
-                if (ti0 > tj0 && 4 * ti0 + 3 < rows_below) {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const double2* p = reinterpret_cast<const double2*>(
-                            &A[(size_t)(j0 + jb + 4 * tj0 + b) * ld + (j0 + jb + 4 * ti0)]);
-                        const double2 lo = p[0], hi = p[1];
-                        old[0][b] = lo.x, old[1][b] = lo.y, old[2][b] = hi.x, old[3][b] = hi.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            const int r = 4 * ti0 + a, c = 4 * tj0 + b;
-                            double v = 0.0;
-                            if (r < m_rows && c < rows_below && c <= r)
-                                v = (r == rows_below) ? y[j0 + jb + c] : A[(size_t)(j0 + jb + c) * ld + (j0 + jb + r)];
-                            old[a][b] = v;
-                        }
-                }
-            }
         }
         __syncthreads();
         TPH(2)
@@ -336,15 +311,19 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                     xr[c] *= Dis[c];
                     prow[c] = xr[c];
                 }
-                if (crank == 0 && rr < m_rows) {
+                // factor output (row-major copy of L and L^-1 b): rows dealt round-robin to the CTAs of the
+                // cluster -- every CTA holds the whole panel -- as 16-byte stores (j0 and ld are multiples of 4)
+                if (rr < m_rows && (rr % csize) == crank) {
+                    if (is_rhs) {
 #pragma unroll
-                    for (int c = 0; c < NB; ++c)
-                        if (c < jb) {
-                            if (is_rhs)
-                                yf[j0 + c] = xr[c];
-                            else
-                                Lf[(size_t)gi * ld + j0 + c] = xr[c];
-                        }
+                        for (int c = 0; c < NB; ++c)
+                            if (c < jb) yf[j0 + c] = xr[c];
+                    } else {
+                        double2* dst = reinterpret_cast<double2*>(&Lf[(size_t)gi * ld + j0]);
+#pragma unroll
+                        for (int c = 0; c < NB; c += 2)
+                            if (c < jb) dst[c >> 1] = make_double2(xr[c], xr[c + 1]);  // columns >= jb are zero padding
+                    }
                 }
             }
         }
@@ -359,11 +338,8 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
 #endif
             for (int t = t_first; t < ntiles; t += gthreads) {
                 int ti, tj;
-                if (t == t_first) {
-                    ti = ti0, tj = tj0;
-                } else {
-                    decode_tile(t, trp, ti, tj);
-                }
+                decode_tile(t, trp, ti, tj);
+                const bool interior = (ti > tj && 4 * ti + 3 < rows_below);
                 double acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -381,23 +357,14 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                     acc[2][0] += vr2 * vc0, acc[2][1] += vr2 * vc1, acc[2][2] += vr2 * vc2, acc[2][3] += vr2 * vc3;
                     acc[3][0] += vr3 * vc0, acc[3][1] += vr3 * vc1, acc[3][2] += vr3 * vc2, acc[3][3] += vr3 * vc3;
                 }
-                const bool pre = (t == t_first);
-                if (ti > tj && 4 * ti + 3 < rows_below) {
+                if (interior) {
                     // interior tile: the 4 rows of a column are 32 contiguous, 16-byte aligned bytes
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         double2* p = reinterpret_cast<double2*>(&A[(size_t)(j0 + jb + 4 * tj + b) * ld + (j0 + jb + 4 * ti)]);
-                        double2 lo, hi;
-                        if (pre) {
-                            lo = make_double2(old[0][b], old[1][b]);
-                            hi = make_double2(old[2][b], old[3][b]);
-                        } else {
-                            lo = p[0];
-                            hi = p[1];
-                        }
-                        lo.x -= acc[0][b], lo.y -= acc[1][b], hi.x -= acc[2][b], hi.y -= acc[3][b];
-                        p[0] = lo;
-                        p[1] = hi;
+                        const double2 lo = p[0], hi = p[1];
+                        p[0] = make_double2(lo.x - acc[0][b], lo.y - acc[1][b]);
+                        p[1] = make_double2(hi.x - acc[2][b], hi.y - acc[3][b]);
                     }
                 } else {
 #pragma unroll
@@ -408,8 +375,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                             if (r >= m_rows || c >= rows_below || c > r) continue;
                             double* p =
                                 (r == rows_below) ? &y[j0 + jb + c] : &A[(size_t)(j0 + jb + c) * ld + (j0 + jb + r)];
-                            const double o = pre ? old[a][b] : *p;
-                            *p = o - acc[a][b];
+                            *p -= acc[a][b];
                         }
                 }
             }

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -152,6 +153,8 @@ struct vilba_ctx {
     // stats
     vilba_stats stats;
     bool profiling = false;
+    std::vector<vilba_ctx*> lanes;  // sub-contexts of vilba_local_ba_batch: independent windows run concurrently
+    int n_lanes = 8;                // env VILBA_BATCH_LANES
     std::vector<cudaEvent_t> probes;  // 6 events per profiled slot
     size_t probes_used = 0;
 };
@@ -647,6 +650,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     ctx->dims.smem_point = ctx->dims.smem_lin = ctx->dims.smem_chol = 0;
     if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->dims.chol_cluster = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VILBA_BATCH_LANES")) ctx->n_lanes = std::max(1, std::atoi(e));
     if (cudaMalloc(&ctx->dwp, sizeof(DevWindow)) != cudaSuccess) {
         delete ctx;
         return nullptr;
@@ -667,6 +671,9 @@ void vilba_destroy(vilba_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (vilba_ctx* sub : ctx->lanes) vilba_destroy(sub);
+    ctx->lanes.clear();
+    cudaSetDevice(ctx->device);
     for (cudaEvent_t e : ctx->probes) cudaEventDestroy(e);
     if (ctx->slot_graph) cudaGraphExecDestroy(ctx->slot_graph);
     if (ctx->dwp) cudaFree(ctx->dwp);
@@ -719,12 +726,43 @@ int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, c
     return r;
 }
 
+// Independent windows (BASELINE config 5): a pool of sub-contexts ("lanes"), each with its own streams, arena
+// and CUDA graph, driven by one host thread per lane.  A single window leaves most of the GPU idle during its
+// latency-bound phases (the 8-CTA Cholesky cluster above all), so concurrent windows fill the machine.
 int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win, vilba_result* out) {
     if (!ctx || n_windows < 0 || (n_windows && (!win || !out))) return VILBA_ERR_ARG;
+    if (n_windows == 0) return VILBA_OK;
+    const int lanes = std::max(1, std::min(ctx->n_lanes, (int)n_windows));
+    while ((int)ctx->lanes.size() < lanes) {
+        vilba_ctx* sub = vilba_create(ctx->device, &ctx->prm);
+        if (!sub) {
+            ctx->err = "could not create a batch lane";
+            return VILBA_ERR_CUDA;
+        }
+        ctx->lanes.push_back(sub);
+    }
+    std::vector<int> status(lanes, VILBA_OK);
+    std::vector<std::thread> th;
+    for (int l = 0; l < lanes; ++l)
+        th.emplace_back([&, l]() {
+            for (int i = l; i < n_windows; i += lanes) {
+                const int r = vilba_local_ba(ctx->lanes[l], &win[i], &out[i], nullptr);
+                if (r < 0) status[l] = r;
+            }
+        });
+    for (auto& t : th) t.join();
     int worst = VILBA_OK;
-    for (int i = 0; i < n_windows; ++i) {
-        int r = vilba_local_ba(ctx, &win[i], &out[i], nullptr);
-        if (r < 0) worst = r;
+    for (int l = 0; l < lanes; ++l) {
+        const vilba_stats& s = ctx->lanes[l]->stats;
+        ctx->stats.kernel_launches += s.kernel_launches;
+        ctx->stats.lm_iterations += s.lm_iterations;
+        ctx->stats.lm_trials += s.lm_trials;
+        ctx->stats.edges_linearized += s.edges_linearized;
+        std::memset(&ctx->lanes[l]->stats, 0, sizeof(vilba_stats));
+        if (status[l] < 0) {
+            worst = status[l];
+            ctx->err = ctx->lanes[l]->err;
+        }
     }
     return worst;
 }
