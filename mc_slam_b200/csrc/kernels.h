@@ -97,13 +97,19 @@ struct DevWindow {
     double* Y;               // E * 24                   per trial: W D^-1 (18) and W (D^-1 b_l) (6)
     const int* blk_edge_i;   // n_free: IMU edge in which the block is key-frame i, or -1
     const int* blk_edge_j;   // n_free: IMU edge in which the block is key-frame j, or -1
-    const int* edge_pt;      // E: map point of every mono edge
+    const int* edge_pt;      // E: map point of every mono edge           (built on the device, pairs.cu)
     int n_pairs;             // n_free (n_free + 1) / 2 key-frame block pairs (a <= b)
     const int* pair_a;       // n_pairs
     const int* pair_b;       // n_pairs
-    const int* pair_begin;   // n_pairs + 1
-    const int* pair_ea;      // (edge of block a, edge of block b) sharing a map point
+    const int* blk_kf;       // n_free: key-frame index of every free block
+    const int* pair_begin;   // n_pairs + 1                                (built on the device)
+    const int* pair_ea;      // (edge of block a, edge of block b) sharing a map point   (built on the device)
     const int* pair_eb;
+    int* edge_pt_rw;         // writable aliases used by the list builder
+    int* pair_begin_rw;
+    int* pair_ea_rw;
+    int* pair_eb_rw;
+    unsigned long long* pt_mask;  // P * 8: 256-bit key-frame masks per map point (all observers | free observers)
     LmState* lm;
     long long* dbg;  // optional debug counters (16 x int64), may be null
     int dbg_flags;   // timing-ablation switches (only honoured by -DVILBA_CHOL_TIMING builds)
@@ -152,6 +158,7 @@ cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, int stage, i
 // [4,5] update+eval
 cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, const DevWindow* wp,
                         const LaunchDims& d, cudaEvent_t* probe);
+cudaError_t launch_build_pair_lists(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_cull(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d, uint8_t* outlier);
 constexpr int kKernelsPerSlot = 10;

@@ -401,7 +401,28 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWi
     double rb = 0.0;
     constexpr int kPerPass = (kSchurThreads / 32) * 5;
     if (live) {
-        for (int t = t0 + warp * 5 + slot; t < t1; t += kPerPass) {
+        // two list entries in flight per lane group: the index -> row loads of both overlap
+        int t = t0 + warp * 5 + slot;
+        for (; t + kPerPass < t1; t += 2 * kPerPass) {
+            const int ea0 = w.pair_ea[t], eb0 = w.pair_eb[t];
+            const int ea1 = w.pair_ea[t + kPerPass], eb1 = w.pair_eb[t + kPerPass];
+            const double* Ya0 = w.Y + 24 * (size_t)ea0;
+            const double* Wb0 = w.W + 18 * (size_t)eb0;
+            const double* Ya1 = w.Y + 24 * (size_t)ea1;
+            const double* Wb1 = w.W + 18 * (size_t)eb1;
+            const double y00 = Ya0[3 * r], y01 = Ya0[3 * r + 1], y02 = Ya0[3 * r + 2];
+            const double y10 = Ya1[3 * r], y11 = Ya1[3 * r + 1], y12 = Ya1[3 * r + 2];
+            double b0[18], b1[18];
+#pragma unroll
+            for (int i = 0; i < 18; ++i) b0[i] = Wb0[i], b1[i] = Wb1[i];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                acc[c] += y00 * b0[3 * c] + y01 * b0[3 * c + 1] + y02 * b0[3 * c + 2];
+                acc[c] += y10 * b1[3 * c] + y11 * b1[3 * c + 1] + y12 * b1[3 * c + 2];
+            }
+            if (diag) rb += Ya0[18 + r] + Ya1[18 + r];
+        }
+        for (; t < t1; t += kPerPass) {
             const int ea = w.pair_ea[t], eb = w.pair_eb[t];
             const double* Ya = w.Y + 24 * (size_t)ea;
             const double* Wb = w.W + 18 * (size_t)eb;

@@ -6,6 +6,7 @@
 // runs in the CUDA kernels of lba_kernels.cu / preint.cu.  There is no CPU fallback: without a usable
 // CUDA device vilba_create() returns NULL.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -65,8 +66,9 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // offsets of one window inside the device arena
 struct Layout {
     // input section (one H2D copy)
-    size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, blk_edge_i, blk_edge_j, edge_pt,
-        pair_a, pair_b, pair_begin, pair_ea, pair_eb, input_end;
+    size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, blk_edge_i, blk_edge_j, blk_kf,
+        pair_a, pair_b, input_end;
+    size_t edge_pt, pair_begin, pair_ea, pair_eb, pt_mask;
     // work section
     size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y, S, Lfac, cminv, cdinv, bs, x, lm, dbg, n_culled,
         outlier, total;
@@ -90,13 +92,15 @@ Layout make_layout(int K, int NI, int P, int E, int n, int n_free, int n_pairs, 
     L.imu_j = take(sizeof(int) * (size_t)NI);
     L.blk_edge_i = take(sizeof(int) * (size_t)n_free);
     L.blk_edge_j = take(sizeof(int) * (size_t)n_free);
-    L.edge_pt = take(sizeof(int) * (size_t)E);
+    L.blk_kf = take(sizeof(int) * (size_t)n_free);
     L.pair_a = take(sizeof(int) * (size_t)n_pairs);
     L.pair_b = take(sizeof(int) * (size_t)n_pairs);
+    L.input_end = o;
+    L.edge_pt = take(sizeof(int) * (size_t)E);
     L.pair_begin = take(sizeof(int) * ((size_t)n_pairs + 1));
     L.pair_ea = take(sizeof(int) * n_triples);
     L.pair_eb = take(sizeof(int) * n_triples);
-    L.input_end = o;
+    L.pt_mask = take(sizeof(unsigned long long) * 8 * (size_t)P);
     for (int b = 0; b < 2; ++b) L.kf_state[b] = take(sizeof(double) * 22 * (size_t)K);
     for (int b = 0; b < 2; ++b) L.pts[b] = take(sizeof(double) * 3 * (size_t)P);
     L.imu_info = take(sizeof(double) * 81 * (size_t)NI);
@@ -194,6 +198,12 @@ int check_window(const vilba_window* w) {
     if (w->n_pts && (w->pt_obs_begin[0] != 0 || w->pt_obs_begin[w->n_pts] != w->n_obs)) return VILBA_ERR_ARG;
     for (int e = 0; e < w->n_obs; ++e)
         if (w->obs_kf[e] < 0 || w->obs_kf[e] >= w->n_kf) return VILBA_ERR_ARG;
+    // observations of a point ordered by key-frame (MapPoint::GetObservations order), each key-frame once
+    for (int p = 0; p < w->n_pts; ++p) {
+        if (w->pt_obs_begin[p + 1] < w->pt_obs_begin[p]) return VILBA_ERR_ARG;
+        for (int e = w->pt_obs_begin[p] + 1; e < w->pt_obs_begin[p + 1]; ++e)
+            if (w->obs_kf[e] <= w->obs_kf[e - 1]) return VILBA_ERR_ARG;
+    }
     return VILBA_OK;
 }
 
@@ -232,6 +242,7 @@ void probe_drain(vilba_ctx* ctx) {
 // flatten + upload: phase A/B of the reference function become "pack into pinned memory, one H2D"
 // ------------------------------------------------------------------------------------------------
 int upload_window(vilba_ctx* ctx, const vilba_window* w) {
+    const auto t_begin = std::chrono::steady_clock::now();
     int st = check_window(w);
     if (st != VILBA_OK) {
         ctx->err = "invalid window";
@@ -258,40 +269,17 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     }
     const int n_pairs = n_free * (n_free + 1) / 2;
     auto pair_index = [n_free](int a, int b) { return a * n_free - a * (a - 1) / 2 + (b - a); };
-    std::vector<int> edge_pt(E), pair_a(n_pairs), pair_b(n_pairs), pair_begin(n_pairs + 1, 0);
+    std::vector<int> pair_a(n_pairs), pair_b(n_pairs), blk_kf(n_free);
     for (int a = 0; a < n_free; ++a)
         for (int b = a; b < n_free; ++b) pair_a[pair_index(a, b)] = a, pair_b[pair_index(a, b)] = b;
-    for (int p = 0; p < P; ++p)
-        for (int ei = w->pt_obs_begin[p]; ei < w->pt_obs_begin[p + 1]; ++ei) {
-            edge_pt[ei] = p;
-            const int bi = kf_block[w->obs_kf[ei]];
-            if (bi < 0) continue;
-            for (int ej = ei; ej < w->pt_obs_begin[p + 1]; ++ej) {
-                const int bj = kf_block[w->obs_kf[ej]];
-                if (bj < 0) continue;
-                if (ej != ei && bi == bj) {
-                    ctx->err = "a map point is observed twice by the same key-frame";
-                    return VILBA_ERR_ARG;
-                }
-                pair_begin[pair_index(bi < bj ? bi : bj, bi < bj ? bj : bi) + 1]++;
-            }
-        }
-    for (int i = 0; i < n_pairs; ++i) pair_begin[i + 1] += pair_begin[i];
-    const size_t n_triples = (size_t)pair_begin[n_pairs];
-    std::vector<int> pair_ea(n_triples), pair_eb(n_triples), fill(pair_begin.begin(), pair_begin.end() - 1);
-    for (int p = 0; p < P; ++p)
-        for (int ei = w->pt_obs_begin[p]; ei < w->pt_obs_begin[p + 1]; ++ei) {
-            const int bi = kf_block[w->obs_kf[ei]];
-            if (bi < 0) continue;
-            for (int ej = ei; ej < w->pt_obs_begin[p + 1]; ++ej) {
-                const int bj = kf_block[w->obs_kf[ej]];
-                if (bj < 0) continue;
-                const bool sw = bj < bi;
-                const int slot = fill[pair_index(sw ? bj : bi, sw ? bi : bj)]++;
-                pair_ea[slot] = sw ? ej : ei;
-                pair_eb[slot] = sw ? ei : ej;
-            }
-        }
+    for (int k = 0; k < K; ++k)
+        if (kf_block[k] >= 0) blk_kf[kf_block[k]] = k;
+    // the (edge_a, edge_b) lists themselves are built on the device (pairs.cu); capacity = sum m (m + 1) / 2
+    size_t n_triples = 0;
+    for (int p = 0; p < P; ++p) {
+        const size_t m = (size_t)(w->pt_obs_begin[p + 1] - w->pt_obs_begin[p]);
+        n_triples += m * (m + 1) / 2;
+    }
     const int lin_ctas = ctx->dims.point_grid;
     const Layout L = make_layout(K, NI, P, E, n, n_free, n_pairs, n_triples, lin_ctas);
     CK(ctx->arena.reserve(L.total), "cudaMalloc(arena)");
@@ -318,16 +306,15 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     }
     std::memcpy(h + L.blk_edge_i, blk_edge_i.data(), sizeof(int) * (size_t)n_free);
     std::memcpy(h + L.blk_edge_j, blk_edge_j.data(), sizeof(int) * (size_t)n_free);
-    if (E) std::memcpy(h + L.edge_pt, edge_pt.data(), sizeof(int) * (size_t)E);
+    std::memcpy(h + L.blk_kf, blk_kf.data(), sizeof(int) * (size_t)n_free);
     std::memcpy(h + L.pair_a, pair_a.data(), sizeof(int) * (size_t)n_pairs);
     std::memcpy(h + L.pair_b, pair_b.data(), sizeof(int) * (size_t)n_pairs);
-    std::memcpy(h + L.pair_begin, pair_begin.data(), sizeof(int) * ((size_t)n_pairs + 1));
-    if (n_triples) {
-        std::memcpy(h + L.pair_ea, pair_ea.data(), sizeof(int) * n_triples);
-        std::memcpy(h + L.pair_eb, pair_eb.data(), sizeof(int) * n_triples);
-    }
     char* d = ctx->arena.base;
+    const auto t_packed = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(d, h, L.input_end, cudaMemcpyHostToDevice, ctx->stream), "H2D window");
+    if (std::getenv("VILBA_DEBUG_COUNTERS"))
+        std::fprintf(stderr, "[vilba dbg] flatten+pair lists %.3f ms, %zu bytes H2D, %zu list entries\n",
+                     std::chrono::duration<double, std::milli>(t_packed - t_begin).count(), L.input_end, n_triples);
 
     DevWindow& dw = ctx->dw;
     std::memset(&dw, 0, sizeof(dw));
@@ -364,6 +351,12 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     dw.pair_begin = reinterpret_cast<const int*>(d + L.pair_begin);
     dw.pair_ea = reinterpret_cast<const int*>(d + L.pair_ea);
     dw.pair_eb = reinterpret_cast<const int*>(d + L.pair_eb);
+    dw.blk_kf = reinterpret_cast<const int*>(d + L.blk_kf);
+    dw.edge_pt_rw = reinterpret_cast<int*>(d + L.edge_pt);
+    dw.pair_begin_rw = reinterpret_cast<int*>(d + L.pair_begin);
+    dw.pair_ea_rw = reinterpret_cast<int*>(d + L.pair_ea);
+    dw.pair_eb_rw = reinterpret_cast<int*>(d + L.pair_eb);
+    dw.pt_mask = reinterpret_cast<unsigned long long*>(d + L.pt_mask);
     dw.S = reinterpret_cast<double*>(d + L.S);
     dw.Lfac = reinterpret_cast<double*>(d + L.Lfac);
     dw.cminv = reinterpret_cast<double*>(d + L.cminv);
@@ -415,6 +408,12 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     std::memcpy(ctx->pinned_small.base, &dw, sizeof(DevWindow));
     CK(cudaMemcpyAsync(ctx->dwp, ctx->pinned_small.base, sizeof(DevWindow), cudaMemcpyHostToDevice, ctx->stream),
        "H2D descriptor");
+    // the list builder reads the working copy of the observation table
+    if (E)
+        CK(cudaMemcpyAsync(d + L.obs, d + L.obs0, sizeof(int4) * (size_t)E, cudaMemcpyDeviceToDevice, ctx->stream),
+           "obs copy");
+    CK(launch_build_pair_lists(ctx->stream, ctx->dwp, ctx->dims), "pair lists");
+    ctx->stats.kernel_launches += 4;
     ctx->has_window = true;
     return VILBA_OK;
 }

@@ -106,6 +106,14 @@ def test_invalid_window_is_rejected(ctx, vilba):
     w.obs_kf[0] = 99
     with pytest.raises(vilba.VilbaError):
         ctx.local_ba(w)
+    # observations of a point must be ordered by key-frame (MapPoint::GetObservations order)
+    w = synth.make_config("tiny")
+    w.obs_kf = w.obs_kf.copy()
+    b = w.pt_obs_begin
+    p = int(np.argmax(np.diff(b) >= 2))
+    w.obs_kf[b[p]], w.obs_kf[b[p] + 1] = w.obs_kf[b[p] + 1], w.obs_kf[b[p]]
+    with pytest.raises(vilba.VilbaError):
+        ctx.local_ba(w)
 
 
 # ---- entry 2 -------------------------------------------------------------------------------------
