@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+NCU_TRAFFIC_LINEARIZE = 8071168  # bytes/launch: dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_full_summary.txt
 METRIC = "local_ba_lm_iters_per_sec"
 UNIT = "LM iters/s"
 
@@ -148,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c3", "c4", "small", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,13 +188,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---- HBM-resident timing --------------------------------------------------------------------
-    ctx.upload(win)
-    for _ in range(W):
-        flush_l2()
-        ctx.solve_resident()
-    ctx.reset_stats()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.start()  # nvidia-smi needs ~1 s to start: sample from the warm-up on (same load), through the timed region
+    ctx.upload(win)
+    t_warm = time.perf_counter()
+    while True:  # at least W warm-up steps and ~1.5 s of load so that the clock samples cover the timed region
+        for _ in range(W):
+            flush_l2()
+            ctx.solve_resident()
+        if time.perf_counter() - t_warm > 1.5:
+            break
+    ctx.reset_stats()
     barrier()
     wall0 = time.perf_counter()
     dev_ms, iters, edges = 0.0, 0, 0
@@ -247,6 +253,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = _peaks()
+        n_red = 15 * win.n_free
         b_lin = algorithmic_bytes_linearize(win)
         lin_us = 1e3 * stp.linearize_ms / max(1, stp.linearize_launches)
         achieved = b_lin / (lin_us * 1e-6) / 1e9 if lin_us > 0 else 0.0
@@ -266,14 +273,34 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "linearize_v2_kernel + reduce_partials + assemble_hpp (linearize_imu_v2 beside it)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(b_lin),
+                         "traffic": NCU_TRAFFIC_LINEARIZE if args.workload == "c3" else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(b_lin),
                          "avg_launch_us": lin_us,
-                         "note": "single 20-KF window: 7.5 MB working set is L2-resident, the kernel is latency-bound"},
+                         "note": "linearize+accumulate (the kernel the north star names); one 20-KF window is a 7 MB, "
+                                 "L2-resident working set, so the kernel is latency-bound; traffic = dram read+write of "
+                                 "linearize_v2_kernel from profiles/r1_ncu_full_summary.txt"},
+            "roofline_dominant": {"kernel": "chol_cluster_kernel", "bound": "fp64 dependent-issue latency",
+                                  "share_of_step": (1e3 * stp.solve_ms / max(1, stp.solve_launches)) * (iters / K) / (1e3 * dev_ms_max / K) if dev_ms_max else None,
+                                  "achieved": (n_red ** 3 / 3.0 + 2.0 * n_red ** 2) / (1e-6 * max(1e-9, 1e3 * stp.solve_ms / max(1, stp.solve_launches))) / 1e12,
+                                  "peak": 37.2, "unit": "TFLOP/s", "peak_source": "148 SMs x 64 FP64 FMA/clk x 1.965 GHz (tools/ubench_fp64.cu measured 61.3/64)",
+                                  "note": "dense Cholesky of the 285x285 reduced camera system on one 8-CTA cluster: n sequential pivots"},
             "kernels_us": {"linearize": lin_us,
                            "schur": 1e3 * stp.schur_ms / max(1, stp.schur_launches),
                            "chol_solve": 1e3 * stp.solve_ms / max(1, stp.solve_launches),
                            "note": "CUDA events around each kernel group in a second, ungraphed pass over the same steps"},
         }
+        if world == 1 and not args.no_batch:
+            # independent windows through vilba_local_ba_batch (BASELINE config 5 shape on one GPU): host buffers in/out
+            nb = 32
+            base = [win] + [synth.make_config(args.workload, window_index=i) for i in range(1, 8)]
+            wins = [base[i % len(base)] for i in range(nb)]
+            ctx.local_ba_batch(wins[:8])
+            t0 = time.perf_counter()
+            rs = ctx.local_ba_batch(wins)
+            tb = time.perf_counter() - t0
+            line["batch"] = {"windows": nb, "lanes": 8, "value": sum(len(r.trace) for r in rs) / tb, "unit": UNIT,
+                             "windows_per_sec": nb / tb,
+                             "note": "vilba_local_ba_batch: independent windows solved concurrently (host buffers, end to end)"}
         if not args.no_cpu_baseline:
             from oracle import pyoracle
             pyoracle.local_ba(win)
