@@ -163,7 +163,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mc_slam_b200 import api, synth
+    from mc_slam_b200 import api, sharding, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the VI local-BA path has no CPU fallback")
@@ -239,17 +239,8 @@ def main():
     d2h = win.kf_state.nbytes + win.pt_xyz.nbytes + win.n_obs + 8 * win.n_obs
 
     # ---- reduce over ranks ----------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s, float(iters), float(e2e_iters), float(edges), float(st.kernel_launches)],
-                     dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    else:
-        tmax, tsum = t, t
-    dev_ms_max, e2e_s_max = float(tmax[0]), float(tmax[1])
-    iters_all, e2e_iters_all, edges_all, launches_all = float(tsum[2]), float(tsum[3]), float(tsum[4]), float(tsum[5])
+    (dev_ms_max, e2e_s_max), (iters_all, e2e_iters_all, edges_all, launches_all) = sharding.reduce_bench(
+        [dev_ms, e2e_s], [float(iters), float(e2e_iters), float(edges), float(st.kernel_launches)], device="cuda")
 
     if rank == 0:
         peak, peak_src = _peaks()
