@@ -31,8 +31,6 @@ namespace vilba {
 
 namespace {
 
-constexpr int NB = kCholNB;   // 16
-constexpr int LDP = NB + 1;   // padded shared-memory row stride of the panel (conflict-free column walks)
 
 // ~1 ulp reciprocal: MUFU seed + two Newton steps (shorter dependent chain than an IEEE division)
 __device__ __forceinline__ double fast_rcp(double d) {
@@ -44,15 +42,16 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return fma(r, e, r);
 }
 
-// LDL^T of a 16x16 block held one row per lane (lane r: a[c] = A(r,c) for c <= r; rows/cols beyond
-// the real size are identity-padded by the caller).  On return lane r holds the unit-lower l(r,c) in
-// a[c], c < r, and d_r in a[r].  `sm` is 16 + 64 doubles of warp-private shared memory.
-__device__ __forceinline__ bool warp_ldlt16_mb4(double (&a)[NB], int lane, double* sm) {
+// LDL^T of an NB x NB block (NB = 16 or 32) held one row per lane (lane r: a[c] = A(r,c) for c <= r; rows/cols
+// beyond the real size are identity-padded by the caller).  On return lane r holds the unit-lower l(r,c) in
+// a[c], c < r, and d_r in a[r].  `sm` is 16 + 4 NB doubles of warp-private shared memory.
+template <int NB>
+__device__ __forceinline__ bool warp_ldlt_mb4(double (&a)[NB], int lane, double* sm) {
     double* Bc = sm;       // 4 x 4  pivot block
-    double* Lb = sm + 16;  // 16 x 4 scaled rows l(r, j..j+3)
+    double* Lb = sm + 16;  // NB x 4 scaled rows l(r, j..j+3)
     bool ok = true;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < NB / 4; ++s) {
         const int j = 4 * s;
         if (lane >= j && lane < j + 4) {
             double* p = Bc + 4 * (lane - j);
@@ -93,7 +92,7 @@ __device__ __forceinline__ bool warp_ldlt16_mb4(double (&a)[NB], int lane, doubl
             a[j + 2] = (i == 2) ? d2 : (i == 3) ? l32 : 0.0;
             a[j + 3] = (i == 3) ? d3 : 0.0;
         }
-        if (s < 3) {
+        if (s < NB / 4 - 1) {
             __syncwarp();
             // trailing part of the block: A(r,c) -= sum_k u(r,k) l(c,k), c = j+4 .. r
 #pragma unroll
@@ -185,7 +184,9 @@ __device__ __forceinline__ void backsub_staged(const double* __restrict__ Lr, in
 
 }  // namespace
 
-__global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWindow* __restrict__ wp) {
+template <int NB>
+__global__ void __launch_bounds__(NB == 32 ? 384 : kCholThreads) chol_cluster_kernel(const DevWindow* __restrict__ wp) {
+    constexpr int LDP = NB + 1;  // padded shared-memory row stride of the panel (conflict-free column walks)
     const DevWindow w = *wp;
     if (w.lm->phase != PH_TRIAL) return;  // uniform over the cluster: nobody reaches a cluster barrier
     cg::cluster_group cluster = cg::this_cluster();
@@ -199,8 +200,8 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
     double* xs = Pn + (size_t)(n + 8) * LDP;  // n   solution during back substitution
     double* Dsq = xs + n;                     // NB  sqrt(d)
     double* Dis = Dsq + NB;                   // NB  1/sqrt(d)
-    double* Wsm = Dis + NB;                   // 80  warp-private scratch of the diagonal factorisation
-    double* Stage = Wsm + 80;                 // 2 x 16 x 321  row stage of the back substitution (n <= 320)
+    double* Wsm = Dis + NB;                   // 16 + 4 NB  warp-private scratch of the diagonal factorisation
+    double* Stage = Wsm + 16 + 4 * NB;                 // 2 x 16 x 321  row stage of the back substitution (n <= 320)
     double* A = w.S;       // working matrix: column block k is only READ in step k, the trailing part is updated
     double* Lf = w.Lfac;   // factor output (same addressing); written by CTA 0, never read inside the loop
     double* y = w.bs;      // rhs row, updated like a matrix row
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
         const int ntiles = trp * (trp + 1) / 2;
         const int gthreads = csize * nwt;
         const int t_first = crank * nwt + wt;
-        double xr0[NB];
+        double xr[NB];  // worker: panel row being solved (the first one is prefetched before the block barrier)
         if (is_factor_warp) {
             // ---- factor warp: (1) load the diagonal block (identity padded), (3) factor, publish ----
             double drow[NB];
@@ -243,9 +244,9 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
             }
             TPH(0)
 #ifdef VILBA_CHOL_TIMING
-            const bool ok = (w.dbg_flags & 4) ? true : warp_ldlt16_mb4(drow, lane, Wsm);
+            const bool ok = (w.dbg_flags & 4) ? true : warp_ldlt_mb4<NB>(drow, lane, Wsm);
 #else
-            const bool ok = warp_ldlt16_mb4(drow, lane, Wsm);
+            const bool ok = warp_ldlt_mb4<NB>(drow, lane, Wsm);
 #endif
             if (!ok && lane == 0) s_fail = 1;
             double dr = 1.0;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
                 const int gi = j0 + jb + rr;
 #pragma unroll
                 for (int c = 0; c < NB; ++c)
-                    xr0[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * ld + gi]) : 0.0;
+                    xr[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * ld + gi]) : 0.0;
             }
         }
         __syncthreads();
@@ -286,13 +287,9 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
         //      bank-conflict free; the rows of the last (partial) group are zero. ----
         if (!is_factor_warp) {
             for (int rr = wt; rr < 4 * trp; rr += nwt) {
-                double xr[NB];
                 const bool is_rhs = (rr == rows_below);
                 const int gi = j0 + jb + rr;
-                if (rr == wt) {
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) xr[c] = xr0[c];
-                } else {
+                if (rr != wt) {
 #pragma unroll
                     for (int c = 0; c < NB; ++c)
                         xr[c] = (rr < m_rows && c < jb) ? (is_rhs ? y[j0 + c] : A[(size_t)(j0 + c) * ld + gi]) : 0.0;
@@ -434,24 +431,31 @@ __global__ void __launch_bounds__(kCholThreads) chol_cluster_kernel(const DevWin
 }
 
 bool chol_has_stage(int n_cap) { return n_cap <= 640; }
+int chol_block_size(int n_cap) { return n_cap <= 640 ? 32 : 16; }  // 32 columns per step while the panel fits in shared memory
 
 size_t chol_smem_bytes(int n) {
+    const size_t nb = (size_t)chol_block_size(n);
     const size_t stage = chol_has_stage(n) ? (size_t)2 * 16 * 321 : 0;
-    return sizeof(double) * ((size_t)NB * NB + (size_t)(n + 8) * LDP + (size_t)n + 2 * NB + 80 + stage);
+    return sizeof(double) * (nb * nb + (size_t)(n + 8) * (nb + 1) + (size_t)n + 2 * nb + 16 + 4 * nb + stage);
 }
 
 cudaError_t configure_chol(const LaunchDims& d) {
-    cudaError_t e = cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_chol);
+    cudaError_t e = cudaFuncSetAttribute(chol_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_chol);
     if (e != cudaSuccess) return e;
-    if (d.chol_cluster > 8)
-        e = cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaFuncSetAttribute(chol_cluster_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_chol);
+    if (e != cudaSuccess) return e;
+    if (d.chol_cluster > 8) {
+        e = cudaFuncSetAttribute(chol_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(chol_cluster_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
     return e;
 }
 
 cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(d.chol_cluster, 1, 1);
-    cfg.blockDim = dim3(kCholThreads, 1, 1);
+    cfg.blockDim = dim3(d.chol_nb == 32 ? 384 : kCholThreads, 1, 1);  // 32-column steps need > 128 registers per thread
     cfg.dynamicSmemBytes = d.smem_chol;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -461,7 +465,8 @@ cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const Launc
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, chol_cluster_kernel, wp);
+    if (d.chol_nb == 32) return cudaLaunchKernelEx(&cfg, chol_cluster_kernel<32>, wp);
+    return cudaLaunchKernelEx(&cfg, chol_cluster_kernel<16>, wp);
 }
 
 }  // namespace vilba

@@ -10,7 +10,6 @@ namespace vilba {
 constexpr int kPreintThreads = 256;
 constexpr int kPointThreads = 256;  // 8 warps per CTA, one warp per map point
 constexpr int kCholThreads = 512;
-constexpr int kCholNB = 16;
 constexpr int kMaxKF = 256;          // key-frames per window supported by the shared-memory stage
 constexpr int kPointGridPerSM = 2;   // CTAs per SM of the grid-stride per-point kernels (fixed grid => graph-capturable)
 constexpr int kImuGrid = 64;         // CTAs (one warp each) of the per-IMU-edge kernels, grid-stride
@@ -139,6 +138,7 @@ struct LaunchDims {
     int sm_count;
     int point_grid;       // kPointGridPerSM * sm_count
     int chol_cluster;     // CTAs of the Cholesky cluster
+    int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
     size_t smem_point;    // dynamic shared memory of update_eval / flags
     size_t smem_lin;      // ... of linearize_v2
     size_t smem_chol;     // ... of chol_cluster
@@ -147,6 +147,7 @@ size_t point_smem_bytes(int K);
 size_t linearize_smem_bytes(int K, int n_free);
 size_t chol_smem_bytes(int n);
 bool chol_has_stage(int n_cap);
+int chol_block_size(int n_cap);
 cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels
 
 cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp);
@@ -154,7 +155,7 @@ cudaError_t launch_eval_initial(cudaStream_t s, const DevWindow* wp, const Launc
 cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, int stage, int max_iters);
 // one slot = [linearize (mono | imu on `side`) -> reduce -> assemble -> iter_begin] if phase == LINEARIZE,
 //            [schur prep -> gather -> cholesky -> update+eval -> decide] if phase == TRIAL
-// `probe` (6 timing events, or NULL): [0,1] linearize+reduce+assemble, [2,3] Schur prep+gather, [3,4] Cholesky,
+// `probe` (8 timing events, or NULL; [6] after schur_prep, [7] after linearize_v2): [0,1] linearize+reduce+assemble, [2,3] Schur prep+gather, [3,4] Cholesky,
 // [4,5] update+eval
 cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, const DevWindow* wp,
                         const LaunchDims& d, cudaEvent_t* probe);

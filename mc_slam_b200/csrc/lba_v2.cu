@@ -510,6 +510,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     linearize_imu_v2_kernel<<<kImuGrid, 32, 0, side>>>(wp);
     if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
     linearize_v2_kernel<<<d.point_grid, kPointThreads, d.smem_lin, s>>>(wp);
+    if (probe && (e = cudaEventRecord(probe[7], s)) != cudaSuccess) return e;
     reduce_partials_kernel<<<d.sm_count, 256, 0, s>>>(wp, d.point_grid);
     if ((e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) return e;
     assemble_hpp_kernel<<<8 * d.sm_count, 256, 0, s>>>(wp);
@@ -518,6 +519,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     // ---- one LM trial (skipped unless phase == TRIAL) ----
     if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
     schur_prep_kernel<<<d.point_grid, 256, 0, s>>>(wp);
+    if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;
     schur_gather_kernel<<<2 * d.sm_count, kSchurThreads, 0, s>>>(wp);
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
     if ((e = launch_chol_cluster(s, wp, d)) != cudaSuccess) return e;

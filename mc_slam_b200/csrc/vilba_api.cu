@@ -161,6 +161,7 @@ struct vilba_ctx {
     int n_lanes = 8;                // env VILBA_BATCH_LANES
     std::vector<cudaEvent_t> probes;  // 6 events per profiled slot
     size_t probes_used = 0;
+    double dbg_ms[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -210,29 +211,34 @@ int check_window(const vilba_window* w) {
 // profiling: six events per slot (see launch_slot); drained after a stream synchronize
 cudaEvent_t* probe_take(vilba_ctx* ctx) {
     if (!ctx->profiling) return nullptr;
-    if (ctx->probes_used + 6 > ctx->probes.size()) {
-        for (int i = 0; i < 6; ++i) {
+    if (ctx->probes_used + 8 > ctx->probes.size()) {
+        for (int i = 0; i < 8; ++i) {
             cudaEvent_t e;
             cudaEventCreate(&e);
             ctx->probes.push_back(e);
         }
     }
     cudaEvent_t* p = &ctx->probes[ctx->probes_used];
-    ctx->probes_used += 6;
+    ctx->probes_used += 8;
     return p;
 }
 void probe_drain(vilba_ctx* ctx) {
-    for (size_t i = 0; i + 6 <= ctx->probes_used; i += 6) {
-        float lin = 0, sch = 0, chol = 0;
+    for (size_t i = 0; i + 8 <= ctx->probes_used; i += 8) {
+        float lin = 0, sch = 0, chol = 0, t = 0;
         cudaEvent_t* p = &ctx->probes[i];
         if (cudaEventElapsedTime(&lin, p[0], p[1]) != cudaSuccess) continue;
         cudaEventElapsedTime(&sch, p[2], p[3]);
         cudaEventElapsedTime(&chol, p[3], p[4]);
         // a slot whose group returned early (nothing to do in that phase) takes a few microseconds
-        if (lin > 0.008f) ctx->stats.linearize_ms += lin, ctx->stats.linearize_launches++;
+        if (lin > 0.008f) {
+            ctx->stats.linearize_ms += lin, ctx->stats.linearize_launches++;
+            if (cudaEventElapsedTime(&t, p[0], p[7]) == cudaSuccess) ctx->dbg_ms[0] += t;  // mono linearize alone
+        }
         if (chol > 0.008f) {
             ctx->stats.schur_ms += sch, ctx->stats.schur_launches++;
             ctx->stats.solve_ms += chol, ctx->stats.solve_launches++;
+            if (cudaEventElapsedTime(&t, p[2], p[6]) == cudaSuccess) ctx->dbg_ms[1] += t;  // schur_prep alone
+            if (cudaEventElapsedTime(&t, p[4], p[5]) == cudaSuccess) ctx->dbg_ms[2] += t;  // update_eval alone
         }
     }
     ctx->probes_used = 0;
@@ -392,6 +398,8 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
         ctx->dims.smem_point = point_smem_bytes(ctx->cap_K);
         ctx->dims.smem_lin = linearize_smem_bytes(ctx->cap_K, ctx->cap_nf);
         ctx->dims.smem_chol = chol_smem_bytes(ctx->cap_n);
+        ctx->dims.chol_nb = chol_block_size(ctx->cap_n);
+        if (const char* e = std::getenv("VILBA_CHOL_NB")) ctx->dims.chol_nb = (std::atoi(e) == 16) ? 16 : ctx->dims.chol_nb;
         if (ctx->dims.smem_lin > 227 * 1024 || ctx->dims.smem_chol > 227 * 1024) {
             ctx->err = "window too large for the shared-memory stages";
             return VILBA_ERR_ARG;
@@ -439,6 +447,11 @@ int reset_window(vilba_ctx* ctx) {
         CK(cudaMemsetAsync(d + L.obs_chi2, 0, sizeof(double) * (size_t)ctx->win_E, s), "reset chi2");
     }
     CK(cudaMemsetAsync(d + L.lm, 0, sizeof(LmState), s), "reset lm");
+    if (std::getenv("VILBA_DEBUG_COUNTERS") && ctx->stats.solve_launches > 0) {
+        std::fprintf(stderr, "[vilba dbg] per launch: linearize_v2 %.1f us, schur_prep %.1f us, update_eval %.1f us\n",
+                     1e3 * ctx->dbg_ms[0] / std::max<long long>(1, ctx->stats.linearize_launches),
+                     1e3 * ctx->dbg_ms[1] / ctx->stats.solve_launches, 1e3 * ctx->dbg_ms[2] / ctx->stats.solve_launches);
+    }
     if (std::getenv("VILBA_DEBUG_COUNTERS")) {
         long long h[16];
         if (cudaMemcpy(h, d + L.dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[8] > 0) {
@@ -646,6 +659,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     ctx->dims.sm_count = ctx->sm_count;
     ctx->dims.point_grid = kPointGridPerSM * ctx->sm_count;
     ctx->dims.chol_cluster = 8;
+    ctx->dims.chol_nb = 32;
     ctx->dims.smem_point = ctx->dims.smem_lin = ctx->dims.smem_chol = 0;
     if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->dims.chol_cluster = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;

@@ -164,3 +164,12 @@ def test_preintegrate_closed_forms_on_device(ctx):
     T = S * h
     assert np.allclose(out[3:6], a * T, rtol=1e-13) and np.allclose(out[0:3], 0.5 * a * T * T, rtol=1e-13)
     assert np.allclose(out[6:15].reshape(3, 3), np.eye(3), atol=1e-15)
+
+
+def test_local_ba_c4_large_window(ctx, oracle):
+    """BASELINE config 4 shape: 100 KF / 50k points / ~600k edges, reduced system n = 1485
+    (16-column Cholesky steps, unknowns of the back substitution in shared memory)."""
+    w = synth.make_config("c4")
+    assert w.n_obs > 550_000 and 15 * w.n_free == 1485
+    r, o = ctx.local_ba(w), oracle.local_ba(w)
+    _compare(r, o, w)
