@@ -92,6 +92,28 @@ class Context:
         self._check(self._lib.vilba_window_download(self._h, C.byref(cr)), "vilba_window_download")
         return res
 
+    # ---- resident batch of independent windows (one batched launch per kernel) --------------------
+    def upload_batch(self, wins: Sequence[Window]):
+        self._keep_batch = list(wins)
+        n = len(wins)
+        cws = (CWindow * n)(*[w.as_c() for w in wins])
+        self._check(self._lib.vilba_batch_upload(self._h, n, cws), "vilba_batch_upload")
+
+    def solve_batch_resident(self) -> List[Result]:
+        n = len(self._keep_batch)
+        crs = (CResult * n)()
+        self._check(self._lib.vilba_batch_solve_resident(self._h, n, crs), "vilba_batch_solve_resident")
+        empty = lambda: Result(kf_state=np.zeros((0, 22)), pt_xyz=np.zeros((0, 3)), obs_outlier=np.zeros(0, np.uint8),
+                               obs_chi2=np.zeros(0))
+        return [empty().take(crs[i]) for i in range(n)]
+
+    def download_batch(self) -> List[Result]:
+        n = len(self._keep_batch)
+        results = [Result.alloc(w) for w in self._keep_batch]
+        crs = (CResult * n)(*[r.as_c() for r in results])
+        self._check(self._lib.vilba_batch_download(self._h, n, crs), "vilba_batch_download")
+        return results
+
     # ---- entry 2: IMUPreintegrator::update loop, batched ----------------------------------------
     def preintegrate_batch(self, sample_begin, gyro, acc, dt, bg, ba) -> np.ndarray:
         sb = np.ascontiguousarray(sample_begin, dtype=np.int32)
@@ -128,6 +150,10 @@ class Context:
 
     def set_profiling(self, on: bool):
         self._lib.vilba_set_profiling(self._h, int(bool(on)))
+
+
+def max_batch() -> int:
+    return int(capi.load_library().vilba_max_batch())
 
 
 def version() -> str:

@@ -303,6 +303,10 @@ EXPORTED_SYMBOLS = [  # every symbol include/vilba.h declares
     "vilba_window_upload",
     "vilba_window_solve_resident",
     "vilba_window_download",
+    "vilba_max_batch",
+    "vilba_batch_upload",
+    "vilba_batch_solve_resident",
+    "vilba_batch_download",
     "vilba_preintegrate_batch",
     "vilba_preintegrate_batch_dev",
     "vilba_get_stats",
@@ -345,6 +349,14 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vilba_window_solve_resident.restype = C.c_int
     lib.vilba_window_download.argtypes = [C.c_void_p, C.POINTER(CResult)]
     lib.vilba_window_download.restype = C.c_int
+    lib.vilba_max_batch.argtypes = []
+    lib.vilba_max_batch.restype = C.c_int
+    lib.vilba_batch_upload.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CWindow)]
+    lib.vilba_batch_upload.restype = C.c_int
+    lib.vilba_batch_solve_resident.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CResult)]
+    lib.vilba_batch_solve_resident.restype = C.c_int
+    lib.vilba_batch_download.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CResult)]
+    lib.vilba_batch_download.restype = C.c_int
     lib.vilba_preintegrate_batch.argtypes = [
         C.c_void_p, C.c_int32, _c_int32_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
         _c_double_p,

@@ -187,7 +187,7 @@ __device__ __forceinline__ void backsub_staged(const double* __restrict__ Lr, in
 template <int NB>
 __global__ void __launch_bounds__(NB == 32 ? 384 : kCholThreads) chol_cluster_kernel(const DevWindow* __restrict__ wp) {
     constexpr int LDP = NB + 1;  // padded shared-memory row stride of the panel (conflict-free column walks)
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_TRIAL) return;  // uniform over the cluster: nobody reaches a cluster barrier
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -454,7 +454,7 @@ cudaError_t configure_chol(const LaunchDims& d) {
 
 cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(d.chol_cluster, 1, 1);
+    cfg.gridDim = dim3(d.chol_cluster, d.n_windows, 1);
     cfg.blockDim = dim3(d.chol_nb == 32 ? 384 : kCholThreads, 1, 1);  // 32-column steps need > 128 registers per thread
     cfg.dynamicSmemBytes = d.smem_chol;
     cfg.stream = s;

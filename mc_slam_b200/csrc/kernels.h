@@ -13,6 +13,7 @@ constexpr int kCholThreads = 512;
 constexpr int kMaxKF = 256;          // key-frames per window supported by the shared-memory stage
 constexpr int kPointGridPerSM = 2;   // CTAs per SM of the grid-stride per-point kernels (fixed grid => graph-capturable)
 constexpr int kImuGrid = 64;         // CTAs (one warp each) of the per-IMU-edge kernels, grid-stride
+constexpr int kMaxBatch = 64;        // windows per batched launch (grid.y)
 
 // obs record: 16 bytes, one vector load per mono edge.
 //   x = bits of float u, y = bits of float v, z = bits of float invSigma2,
@@ -66,6 +67,15 @@ struct DevWindow {
     // estimates, double buffered (index LmState::cur = accepted state, 1-cur = trial state)
     double* kf_state[2];  // K * 22
     double* pts[2];       // P * 3
+    const double* kf_state0;  // uploaded initial estimates (every solve restarts from them)
+    const double* pts0;
+    const int4* obs0;
+    uint8_t* outlier;     // E: final outlier flags
+    // packed results of this window inside the batch's output region (one D2H for the whole batch)
+    double* out_kf_state;
+    double* out_pts;
+    double* out_chi2;
+    uint8_t* out_outlier;
     const int* kf_block;  // K: block index among free key-frames, -1 if fixed
     // imu edges
     const int* imu_i;
@@ -136,7 +146,12 @@ cudaError_t launch_preint_batch(cudaStream_t stream, int n_pairs, const int* sam
 // change between windows and one LM "slot" can be captured once in a CUDA graph.
 struct LaunchDims {
     int sm_count;
-    int point_grid;       // kPointGridPerSM * sm_count
+    int n_windows;        // grid.y: windows solved by one launch
+    int point_grid;       // grid.x of the per-point kernels (per window)
+    int imu_grid;         // grid.x of the per-IMU-edge kernels
+    int gather_grid;      // grid.x of the Schur gather (CTAs of 1024 threads looping over block pairs)
+    int reduce_grid;      // grid.x of reduce_partials
+    int assemble_grid;    // grid.x of assemble_hpp
     int chol_cluster;     // CTAs of the Cholesky cluster
     int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
     size_t smem_point;    // dynamic shared memory of update_eval / flags
@@ -150,9 +165,11 @@ bool chol_has_stage(int n_cap);
 int chol_block_size(int n_cap);
 cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels
 
-cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp);
+cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_reset(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_export(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_eval_initial(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);  // eval at the current state
-cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, int stage, int max_iters);
+cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, const LaunchDims& d, int stage, int max_iters);
 // one slot = [linearize (mono | imu on `side`) -> reduce -> assemble -> iter_begin] if phase == LINEARIZE,
 //            [schur prep -> gather -> cholesky -> update+eval -> decide] if phase == TRIAL
 // `probe` (8 timing events, or NULL; [6] after schur_prep, [7] after linearize_v2): [0,1] linearize+reduce+assemble, [2,3] Schur prep+gather, [3,4] Cholesky,
@@ -161,7 +178,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
                         const LaunchDims& d, cudaEvent_t* probe);
 cudaError_t launch_build_pair_lists(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_cull(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
-cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d, uint8_t* outlier);
+cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 constexpr int kKernelsPerSlot = 10;
 
 }  // namespace vilba

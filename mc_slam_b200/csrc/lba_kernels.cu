@@ -30,7 +30,7 @@ __device__ __forceinline__ double group8_sum(double v) {
 
 template <bool APPLY>
 __global__ void __launch_bounds__(kPointThreads) update_eval_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (APPLY && w.lm->phase != PH_TRIAL) return;
     extern __shared__ double smem[];
     const KfSmem ks = kf_smem_carve(smem, w.K);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kPointThreads) update_eval_kernel(const DevWin
 // Gauss-Jordan with partial pivoting, one warp per edge (lane = column of the augmented matrix).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) imu_prepare_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     __shared__ double A[9][18];
     const int lane = threadIdx.x;
     for (int e = blockIdx.x; e < w.NI; e += gridDim.x) {
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32) imu_prepare_kernel(const DevWindow* __rest
 // ------------------------------------------------------------------------------------------------
 // after the stage's initial computeActiveErrors: currentChi, iteration counter, phase
 __global__ void lm_stage_begin_kernel(const DevWindow* __restrict__ wp, int stage, int max_iters) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (threadIdx.x == 0) {
         LmState* s = w.lm;
         s->current_chi = s->chi_acc;  // currentChi = activeRobustChi2() at the stage's first iteration
@@ -213,7 +213,7 @@ __global__ void lm_stage_begin_kernel(const DevWindow* __restrict__ wp, int stag
 }
 
 __global__ void __launch_bounds__(256) lm_iter_begin_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     LmState* s = w.lm;
     if (s->phase != PH_LINEARIZE) return;
     __shared__ double red[8];
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) lm_iter_begin_kernel(const DevWindow* __r
 }
 
 __global__ void __launch_bounds__(32) lm_decide_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     LmState* s = w.lm;
     if (s->phase != PH_TRIAL) return;
     const double lambda = s->lambda;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(32) lm_decide_kernel(const DevWindow* __restri
 // ------------------------------------------------------------------------------------------------
 template <bool CULL>
 __global__ void __launch_bounds__(kPointThreads) flags_kernel(const DevWindow* __restrict__ wp, uint8_t* outlier) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     extern __shared__ double smem[];
     const KfSmem ks = kf_smem_carve(smem, w.K);
     const int cur = w.lm->cur;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kPointThreads) flags_kernel(const DevWindow* _
                 r.w &= ~OBS_ROBUST;  // e->setRobustKernel(0) on every mono edge
                 w.obs[e] = r;
             } else {
-                outlier[e] = bad ? 1 : 0;
+                w.outlier[e] = bad ? 1 : 0;
             }
         }
     }
@@ -347,40 +347,77 @@ __global__ void __launch_bounds__(kPointThreads) flags_kernel(const DevWindow* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// reset (restart every window from its uploaded initial state) and export (pack the results of every
+// window into one contiguous region => one D2H copy for the whole batch)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reset_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = wp[blockIdx.y];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < 22 * w.K; i += nt) w.kf_state[0][i] = w.kf_state[1][i] = w.kf_state0[i];
+    for (int i = tid; i < 3 * w.P; i += nt) w.pts[0][i] = w.pts[1][i] = w.pts0[i];
+    for (int i = tid; i < w.E; i += nt) {
+        w.obs[i] = w.obs0[i];
+        w.obs_chi2[i] = 0.0;
+    }
+    int* lm = reinterpret_cast<int*>(w.lm);
+    for (int i = tid; i < (int)(sizeof(LmState) / sizeof(int)); i += nt) lm[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) export_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow w = wp[blockIdx.y];
+    const int cur = w.lm->cur;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < 22 * w.K; i += nt) w.out_kf_state[i] = w.kf_state[cur][i];
+    for (int i = tid; i < 3 * w.P; i += nt) w.out_pts[i] = w.pts[cur][i];
+    for (int i = tid; i < w.E; i += nt) {
+        w.out_chi2[i] = w.obs_chi2[i];
+        w.out_outlier[i] = w.outlier[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 size_t point_smem_bytes(int K) { return kf_smem_bytes(K); }
 
-cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp) {
-    imu_prepare_kernel<<<kImuGrid, 32, 0, s>>>(wp);
+cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    imu_prepare_kernel<<<dim3(d.imu_grid, d.n_windows), 32, 0, s>>>(wp);
     return cudaGetLastError();
 }
 cudaError_t launch_eval_initial(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
-    update_eval_kernel<false><<<d.point_grid, kPointThreads, d.smem_point, s>>>(wp);
+    update_eval_kernel<false><<<dim3(d.point_grid, d.n_windows), kPointThreads, d.smem_point, s>>>(wp);
     return cudaGetLastError();
 }
 cudaError_t launch_update_eval_apply(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
-    update_eval_kernel<true><<<d.point_grid, kPointThreads, d.smem_point, s>>>(wp);
+    update_eval_kernel<true><<<dim3(d.point_grid, d.n_windows), kPointThreads, d.smem_point, s>>>(wp);
     return cudaGetLastError();
 }
-cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, int stage, int max_iters) {
-    lm_stage_begin_kernel<<<1, 32, 0, s>>>(wp, stage, max_iters);
+cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, const LaunchDims& d, int stage, int max_iters) {
+    lm_stage_begin_kernel<<<dim3(1, d.n_windows), 32, 0, s>>>(wp, stage, max_iters);
     return cudaGetLastError();
 }
-cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp) {
-    lm_iter_begin_kernel<<<1, 256, 0, s>>>(wp);
+cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    lm_iter_begin_kernel<<<dim3(1, d.n_windows), 256, 0, s>>>(wp);
     return cudaGetLastError();
 }
-cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp) {
-    lm_decide_kernel<<<1, 32, 0, s>>>(wp);
+cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    lm_decide_kernel<<<dim3(1, d.n_windows), 32, 0, s>>>(wp);
     return cudaGetLastError();
 }
 cudaError_t launch_cull(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
-    flags_kernel<true><<<d.point_grid, kPointThreads, d.smem_point, s>>>(wp, nullptr);
+    flags_kernel<true><<<dim3(d.point_grid, d.n_windows), kPointThreads, d.smem_point, s>>>(wp, nullptr);
     return cudaGetLastError();
 }
-cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d, uint8_t* outlier) {
-    flags_kernel<false><<<d.point_grid, kPointThreads, d.smem_point, s>>>(wp, outlier);
+cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    flags_kernel<false><<<dim3(d.point_grid, d.n_windows), kPointThreads, d.smem_point, s>>>(wp, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t launch_reset(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    reset_kernel<<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
+    return cudaGetLastError();
+}
+cudaError_t launch_export(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    export_kernel<<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
     return cudaGetLastError();
 }
 cudaError_t configure_point_kernels(const LaunchDims& d) {

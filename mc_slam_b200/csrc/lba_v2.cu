@@ -24,7 +24,7 @@ size_t linearize_v2_smem_bytes(int K, int n_free, int warps) {
 }
 
 __global__ void __launch_bounds__(32) linearize_imu_v2_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_LINEARIZE) return;
     // one warp per IMU edge pair (EdgeNavStatePVR + EdgeNavStateBias)
     __shared__ double J[216];   // 9 x 24: PVR_i (9) | Bias_i (6) | PVR_j (9)
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(32) linearize_imu_v2_kernel(const DevWindow* _
 }
 
 __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_LINEARIZE) return;
     const int point_ctas = gridDim.x;
     extern __shared__ double smem[];
@@ -284,7 +284,7 @@ __device__ __forceinline__ int pose6_index(int o) {  // offset inside a 15-block
 
 // fixed-order reduction of the CTA partials: one warp per entry (lane-strided partial sums, xor tree)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const DevWindow* __restrict__ wp, int point_ctas) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_LINEARIZE) return;
     const int entries = w.n_free * kAccStride;
     const int lane = threadIdx.x & 31;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const DevWindow* _
 }
 
 __global__ void __launch_bounds__(256) assemble_hpp_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_LINEARIZE) return;
     const int n = w.n;
     const size_t total = (size_t)n * n + n;
@@ -360,7 +360,7 @@ constexpr int kSchurThreads = 1024;  // 32 warps x 5 (edge_a, edge_b) pairs per 
 
 // per trial: Y_e = W_e D_l^-1 (BDinv, block_solver.hpp:407) and Wc_e = W_e (D_l^-1 b_l) for every mono edge
 __global__ void __launch_bounds__(256) schur_prep_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_TRIAL) return;
     const double lambda = w.lm->lambda;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < w.E; e += gridDim.x * blockDim.x) {
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256) schur_prep_kernel(const DevWindow* __rest
 // 6x6 product Y_a W_b^T of its entry, so the 6 lanes of an entry read Y_a (144 B) and W_b (144 B) as
 // coalesced, L1-broadcast lines instead of 42 scattered 8-byte loads per thread.
 __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_TRIAL) return;
     __shared__ double red[kSchurThreads / 32][42];
     __shared__ double blockacc[42];
@@ -486,8 +486,8 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWi
 size_t linearize_smem_bytes(int K, int n_free) { return linearize_v2_smem_bytes(K, n_free, kPointThreads / 32); }
 
 cudaError_t launch_update_eval_apply(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
-cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp);
-cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp);
+cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t configure_point_kernels(const LaunchDims& d);
 cudaError_t configure_chol(const LaunchDims& d);
@@ -507,26 +507,26 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     // ---- linearise (skipped on the device unless phase == LINEARIZE): IMU edges beside the mono edges ----
     if ((e = cudaEventRecord(fork, s)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
-    linearize_imu_v2_kernel<<<kImuGrid, 32, 0, side>>>(wp);
+    linearize_imu_v2_kernel<<<dim3(d.imu_grid, d.n_windows), 32, 0, side>>>(wp);
     if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
-    linearize_v2_kernel<<<d.point_grid, kPointThreads, d.smem_lin, s>>>(wp);
+    linearize_v2_kernel<<<dim3(d.point_grid, d.n_windows), kPointThreads, d.smem_lin, s>>>(wp);
     if (probe && (e = cudaEventRecord(probe[7], s)) != cudaSuccess) return e;
-    reduce_partials_kernel<<<d.sm_count, 256, 0, s>>>(wp, d.point_grid);
+    reduce_partials_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.point_grid);
     if ((e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) return e;
-    assemble_hpp_kernel<<<8 * d.sm_count, 256, 0, s>>>(wp);
+    assemble_hpp_kernel<<<dim3(d.assemble_grid, d.n_windows), 256, 0, s>>>(wp);
     if (probe && (e = cudaEventRecord(probe[1], s)) != cudaSuccess) return e;
-    if ((e = launch_lm_iter_begin(s, wp)) != cudaSuccess) return e;
+    if ((e = launch_lm_iter_begin(s, wp, d)) != cudaSuccess) return e;
     // ---- one LM trial (skipped unless phase == TRIAL) ----
     if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
-    schur_prep_kernel<<<d.point_grid, 256, 0, s>>>(wp);
+    schur_prep_kernel<<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
     if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;
-    schur_gather_kernel<<<2 * d.sm_count, kSchurThreads, 0, s>>>(wp);
+    schur_gather_kernel<<<dim3(d.gather_grid, d.n_windows), kSchurThreads, 0, s>>>(wp);
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
     if ((e = launch_chol_cluster(s, wp, d)) != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;
     if ((e = launch_update_eval_apply(s, wp, d)) != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[5], s)) != cudaSuccess) return e;
-    if ((e = launch_lm_decide(s, wp)) != cudaSuccess) return e;
+    if ((e = launch_lm_decide(s, wp, d)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

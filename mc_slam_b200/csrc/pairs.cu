@@ -24,7 +24,7 @@ __device__ __forceinline__ int mask_rank(const unsigned long long* m, int k) {  
 
 // one thread per map point: mask of all observing key-frames, mask of the free ones, edge -> point table
 __global__ void __launch_bounds__(256) pair_masks_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < w.P; p += gridDim.x * blockDim.x) {
         unsigned long long all[kMaskWords] = {0, 0, 0, 0}, fr[kMaskWords] = {0, 0, 0, 0};
         for (int e = w.pt_obs_begin[p]; e < w.pt_obs_begin[p + 1]; ++e) {
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) pair_masks_kernel(const DevWindow* __rest
 // one warp per block pair; FILL = false counts, FILL = true writes the entries
 template <bool FILL>
 __global__ void __launch_bounds__(256) pair_lists_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     const int lane = threadIdx.x & 31;
     const int nw = gridDim.x * (blockDim.x >> 5);
     for (int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pair < w.n_pairs; pair += nw) {
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) pair_lists_kernel(const DevWindow* __rest
 
 // exclusive scan of the counts (single warp, chunks of 32)
 __global__ void __launch_bounds__(32) pair_scan_kernel(const DevWindow* __restrict__ wp) {
-    const DevWindow w = *wp;
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
     const int lane = threadIdx.x;
     int carry = 0;
     if (lane == 0) w.pair_begin_rw[0] = 0;
@@ -88,10 +88,10 @@ __global__ void __launch_bounds__(32) pair_scan_kernel(const DevWindow* __restri
 }
 
 cudaError_t launch_build_pair_lists(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
-    pair_masks_kernel<<<d.point_grid, 256, 0, s>>>(wp);
-    pair_lists_kernel<false><<<d.point_grid, 256, 0, s>>>(wp);
-    pair_scan_kernel<<<1, 32, 0, s>>>(wp);
-    pair_lists_kernel<true><<<d.point_grid, 256, 0, s>>>(wp);
+    pair_masks_kernel<<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
+    pair_lists_kernel<false><<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
+    pair_scan_kernel<<<dim3(1, d.n_windows), 32, 0, s>>>(wp);
+    pair_lists_kernel<true><<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
     return cudaGetLastError();
 }
 

@@ -3,8 +3,12 @@
 // The host side mirrors the control flow of Optimizer::LocalBundleAdjustmentNavState phases C..E
 // (src/Optimizer.cpp:2643-2701) and of SparseOptimizer::optimize / OptimizationAlgorithmLevenberg::solve
 // (g2o/core/sparse_optimizer.cpp:354-419, optimization_algorithm_levenberg.cpp:61-164); all arithmetic
-// runs in the CUDA kernels of lba_kernels.cu / preint.cu.  There is no CPU fallback: without a usable
-// CUDA device vilba_create() returns NULL.
+// runs in the CUDA kernels of lba_kernels.cu / lba_v2.cu / chol.cu / preint.cu.  There is no CPU fallback:
+// without a usable CUDA device vilba_create() returns NULL.
+//
+// A context holds a *batch* of 1..kMaxBatch independent windows.  Every kernel is launched once for the
+// whole batch (grid.y = window), each window carries its own device-resident LM controller, and a window
+// that has finished simply returns early from the remaining launches.  A single window is a batch of one.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -63,18 +67,28 @@ struct Pinned {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-// offsets of one window inside the device arena
+// offsets of one window inside the three regions of the device arena
 struct Layout {
-    // input section (one H2D copy)
+    // input region (all windows contiguous => one H2D copy per batch); offsets relative to in_base
     size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, blk_edge_i, blk_edge_j, blk_kf,
-        pair_a, pair_b, input_end;
+        pair_a, pair_b, in_bytes;
+    // output region (all windows contiguous => one D2H copy per batch); offsets relative to out_base
+    size_t o_kf, o_pts, o_chi2, o_outlier, out_bytes;
+    // work region; offsets relative to wk_base
     size_t edge_pt, pair_begin, pair_ea, pair_eb, pt_mask;
-    // work section
-    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y, S, Lfac, cminv, cdinv, bs, x, lm, dbg, n_culled,
-        outlier, total;
+    size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y,
+        S, Lfac, cminv, cdinv, bs, x, dbg, outlier, wk_bytes;
 };
 
-Layout make_layout(int K, int NI, int P, int E, int n, int n_free, int n_pairs, size_t n_triples, int lin_ctas) {
+struct WinMeta {
+    int K = 0, NI = 0, P = 0, E = 0, n_free = 0, n = 0, n_pairs = 0;
+    size_t n_triples = 0;
+    Layout L;
+    size_t in_base = 0, out_base = 0, wk_base = 0;
+};
+
+Layout make_layout(const WinMeta& m, int lin_ctas) {
+    const size_t K = m.K, NI = m.NI, P = m.P, E = m.E, n = m.n, n_free = m.n_free, n_pairs = m.n_pairs;
     Layout L;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -82,54 +96,64 @@ Layout make_layout(int K, int NI, int P, int E, int n, int n_free, int n_pairs, 
         o = align_up(o + bytes);
         return at;
     };
-    L.kf_state0 = take(sizeof(double) * 22 * (size_t)K);
-    L.pts0 = take(sizeof(double) * 3 * (size_t)P);
-    L.imu_preint = take(sizeof(double) * 142 * (size_t)NI);
-    L.obs0 = take(sizeof(int4) * (size_t)E);
-    L.pt_obs_begin = take(sizeof(int) * ((size_t)P + 1));
-    L.kf_block = take(sizeof(int) * (size_t)K);
-    L.imu_i = take(sizeof(int) * (size_t)NI);
-    L.imu_j = take(sizeof(int) * (size_t)NI);
-    L.blk_edge_i = take(sizeof(int) * (size_t)n_free);
-    L.blk_edge_j = take(sizeof(int) * (size_t)n_free);
-    L.blk_kf = take(sizeof(int) * (size_t)n_free);
-    L.pair_a = take(sizeof(int) * (size_t)n_pairs);
-    L.pair_b = take(sizeof(int) * (size_t)n_pairs);
-    L.input_end = o;
-    L.edge_pt = take(sizeof(int) * (size_t)E);
-    L.pair_begin = take(sizeof(int) * ((size_t)n_pairs + 1));
-    L.pair_ea = take(sizeof(int) * n_triples);
-    L.pair_eb = take(sizeof(int) * n_triples);
-    L.pt_mask = take(sizeof(unsigned long long) * 8 * (size_t)P);
-    for (int b = 0; b < 2; ++b) L.kf_state[b] = take(sizeof(double) * 22 * (size_t)K);
-    for (int b = 0; b < 2; ++b) L.pts[b] = take(sizeof(double) * 3 * (size_t)P);
-    L.imu_info = take(sizeof(double) * 81 * (size_t)NI);
-    L.imu_err = take(sizeof(double) * 15 * (size_t)NI);
-    L.obs = take(sizeof(int4) * (size_t)E);
-    L.obs_chi2 = take(sizeof(double) * (size_t)E);
-    L.Hpp = take(sizeof(double) * (size_t)n * n);
-    L.bp = take(sizeof(double) * (size_t)n);
-    L.Hll = take(sizeof(double) * 6 * (size_t)P);
-    L.bl = take(sizeof(double) * 3 * (size_t)P);
-    L.W = take(sizeof(double) * 18 * (size_t)E);
-    L.lin_partial = take(sizeof(double) * 27 * (size_t)n_free * lin_ctas);
-    L.imu_slot = take(sizeof(double) * 930 * (size_t)NI);
-    L.mono_sum = take(sizeof(double) * 27 * (size_t)n_free);
-    L.Y = take(sizeof(double) * 24 * (size_t)E);
-    const size_t lds = ((size_t)n + 3) & ~(size_t)3;
+    L.kf_state0 = take(sizeof(double) * 22 * K);
+    L.pts0 = take(sizeof(double) * 3 * P);
+    L.imu_preint = take(sizeof(double) * 142 * NI);
+    L.obs0 = take(sizeof(int4) * E);
+    L.pt_obs_begin = take(sizeof(int) * (P + 1));
+    L.kf_block = take(sizeof(int) * K);
+    L.imu_i = take(sizeof(int) * NI);
+    L.imu_j = take(sizeof(int) * NI);
+    L.blk_edge_i = take(sizeof(int) * n_free);
+    L.blk_edge_j = take(sizeof(int) * n_free);
+    L.blk_kf = take(sizeof(int) * n_free);
+    L.pair_a = take(sizeof(int) * n_pairs);
+    L.pair_b = take(sizeof(int) * n_pairs);
+    L.in_bytes = o;
+    o = 0;
+    L.o_kf = take(sizeof(double) * 22 * K);
+    L.o_pts = take(sizeof(double) * 3 * P);
+    L.o_chi2 = take(sizeof(double) * E);
+    L.o_outlier = take(E);
+    L.out_bytes = o;
+    o = 0;
+    L.edge_pt = take(sizeof(int) * E);
+    L.pair_begin = take(sizeof(int) * (n_pairs + 1));
+    L.pair_ea = take(sizeof(int) * m.n_triples);
+    L.pair_eb = take(sizeof(int) * m.n_triples);
+    L.pt_mask = take(sizeof(unsigned long long) * 8 * P);
+    for (int b = 0; b < 2; ++b) L.kf_state[b] = take(sizeof(double) * 22 * K);
+    for (int b = 0; b < 2; ++b) L.pts[b] = take(sizeof(double) * 3 * P);
+    L.imu_info = take(sizeof(double) * 81 * NI);
+    L.imu_err = take(sizeof(double) * 15 * NI);
+    L.obs = take(sizeof(int4) * E);
+    L.obs_chi2 = take(sizeof(double) * E);
+    L.Hpp = take(sizeof(double) * n * n);
+    L.bp = take(sizeof(double) * n);
+    L.Hll = take(sizeof(double) * 6 * P);
+    L.bl = take(sizeof(double) * 3 * P);
+    L.W = take(sizeof(double) * 18 * E);
+    L.lin_partial = take(sizeof(double) * 27 * n_free * (size_t)lin_ctas);
+    L.imu_slot = take(sizeof(double) * 930 * NI);
+    L.mono_sum = take(sizeof(double) * 27 * n_free);
+    L.Y = take(sizeof(double) * 24 * E);
+    const size_t lds = (n + 3) & ~(size_t)3;
     L.S = take(sizeof(double) * lds * n);
     L.Lfac = take(sizeof(double) * lds * n);
-    L.cminv = take(sizeof(double) * 256 * ((size_t)n / 16 + 2));
-    L.cdinv = take(sizeof(double) * (size_t)n);
-    L.bs = take(sizeof(double) * (size_t)n);
-    L.x = take(sizeof(double) * (size_t)n);
-    L.lm = take(sizeof(LmState));
+    L.cminv = take(sizeof(double) * 256 * (n / 16 + 2));
+    L.cdinv = take(sizeof(double) * n);
+    L.bs = take(sizeof(double) * n);
+    L.x = take(sizeof(double) * n);
     L.dbg = take(sizeof(long long) * 16);
-    L.n_culled = take(sizeof(int) * 4);
-    L.outlier = take((size_t)E);
-    L.total = o;
+    L.outlier = take(E);
+    L.wk_bytes = o;
     return L;
 }
+
+struct GraphEntry {
+    LaunchDims dims;
+    cudaGraphExec_t exec;
+};
 
 }  // namespace
 
@@ -140,26 +164,27 @@ struct vilba_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr;
     vilba_params prm;
     Arena arena, preint_arena;
-    Pinned pinned, pinned_small;
+    Pinned pinned, pinned_out, pinned_small;
     std::string err;
     int sm_count = 148;
-    // resident window
-    bool has_window = false;
-    Layout L;
-    DevWindow dw;             // host copy
-    DevWindow* dwp = nullptr; // device copy the kernels read (fixed address => graph-capturable launches)
+    int max_batch = kMaxBatch;
+    // resident batch
+    int n_win = 0;
+    std::vector<WinMeta> meta;
+    std::vector<DevWindow> dw;  // host copies
+    DevWindow* dwp = nullptr;   // device array the kernels read (fixed address => graph-capturable launches)
+    size_t in_total = 0, out_total = 0, lm_base = 0, out_region = 0;  // arena: [in | out | lm array | work]
     LaunchDims dims;
-    int cap_K = 0, cap_nf = 0, cap_n = 0;  // capacities the shared-memory sizes / the graph were built for
-    cudaGraphExec_t slot_graph = nullptr;
-    bool use_graph = true;   // env VILBA_GRAPH=0 launches the slot kernels one by one
-    int win_E = 0, win_NI = 0, win_P = 0, win_K = 0;
-    int last_cur = 0;        // estimate buffer that holds the result of the last solve
+    int chol_cluster = 8;
+    int cap_K = 0, cap_nf = 0, cap_n = 0;  // capacities the shared-memory sizes were configured for
+    std::vector<GraphEntry> graphs;        // one captured LM slot per launch geometry
+    bool use_graph = true;                 // env VILBA_GRAPH=0 launches the slot kernels one by one
     // stats
     vilba_stats stats;
     bool profiling = false;
-    std::vector<vilba_ctx*> lanes;  // sub-contexts of vilba_local_ba_batch: independent windows run concurrently
-    int n_lanes = 8;                // env VILBA_BATCH_LANES
-    std::vector<cudaEvent_t> probes;  // 6 events per profiled slot
+    std::vector<vilba_ctx*> lanes;  // sub-contexts of vilba_local_ba_batch: chunks of the batch are pipelined over them
+    int n_lanes = 2;                // env VILBA_BATCH_LANES
+    std::vector<cudaEvent_t> probes;  // 8 events per profiled slot
     size_t probes_used = 0;
     double dbg_ms[4] = {0, 0, 0, 0};
 };
@@ -197,6 +222,7 @@ int check_window(const vilba_window* w) {
         if (!(w->kf_flags[i] & VILBA_KF_HAS_BIAS) || !(w->kf_flags[j] & VILBA_KF_HAS_BIAS)) return VILBA_ERR_ARG;
     }
     if (w->n_pts && (w->pt_obs_begin[0] != 0 || w->pt_obs_begin[w->n_pts] != w->n_obs)) return VILBA_ERR_ARG;
+    if (!w->n_pts && w->n_obs) return VILBA_ERR_ARG;
     for (int e = 0; e < w->n_obs; ++e)
         if (w->obs_kf[e] < 0 || w->obs_kf[e] >= w->n_kf) return VILBA_ERR_ARG;
     // observations of a point ordered by key-frame (MapPoint::GetObservations order), each key-frame once
@@ -208,7 +234,7 @@ int check_window(const vilba_window* w) {
     return VILBA_OK;
 }
 
-// profiling: six events per slot (see launch_slot); drained after a stream synchronize
+// profiling: eight events per slot (see launch_slot); drained after a stream synchronize
 cudaEvent_t* probe_take(vilba_ctx* ctx) {
     if (!ctx->profiling) return nullptr;
     if (ctx->probes_used + 8 > ctx->probes.size()) {
@@ -230,11 +256,11 @@ void probe_drain(vilba_ctx* ctx) {
         cudaEventElapsedTime(&sch, p[2], p[3]);
         cudaEventElapsedTime(&chol, p[3], p[4]);
         // a slot whose group returned early (nothing to do in that phase) takes a few microseconds
-        if (lin > 0.008f) {
+        if (lin > 0.008f * ctx->n_win) {
             ctx->stats.linearize_ms += lin, ctx->stats.linearize_launches++;
             if (cudaEventElapsedTime(&t, p[0], p[7]) == cudaSuccess) ctx->dbg_ms[0] += t;  // mono linearize alone
         }
-        if (chol > 0.008f) {
+        if (chol > 0.008f * ctx->n_win) {
             ctx->stats.schur_ms += sch, ctx->stats.schur_launches++;
             ctx->stats.solve_ms += chol, ctx->stats.solve_launches++;
             if (cudaEventElapsedTime(&t, p[2], p[6]) == cudaSuccess) ctx->dbg_ms[1] += t;  // schur_prep alone
@@ -244,53 +270,32 @@ void probe_drain(vilba_ctx* ctx) {
     ctx->probes_used = 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// flatten + upload: phase A/B of the reference function become "pack into pinned memory, one H2D"
-// ------------------------------------------------------------------------------------------------
-int upload_window(vilba_ctx* ctx, const vilba_window* w) {
-    const auto t_begin = std::chrono::steady_clock::now();
-    int st = check_window(w);
-    if (st != VILBA_OK) {
-        ctx->err = "invalid window";
-        return st;
-    }
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    const int K = w->n_kf, NI = w->n_imu, P = w->n_pts, E = w->n_obs;
-    std::vector<int> kf_block(K, -1);
-    int n_free = 0;
-    for (int k = 0; k < K; ++k)
-        if (!(w->kf_flags[k] & VILBA_KF_FIXED)) kf_block[k] = n_free++;
-    const int n = 15 * n_free;
-    // v2 accumulation structures: IMU edge of every block, map point of every edge, and per key-frame
-    // block pair (a <= b) the list of (edge_a, edge_b) that share a map point
-    std::vector<int> blk_edge_i(n_free, -1), blk_edge_j(n_free, -1);
-    for (int e = 0; e < NI; ++e) {
-        const int bi = kf_block[w->imu_kf_i[e]], bj = kf_block[w->imu_kf_j[e]];
-        if ((bi >= 0 && blk_edge_i[bi] >= 0) || (bj >= 0 && blk_edge_j[bj] >= 0) || (bi >= 0 && bi == bj)) {
-            ctx->err = "a key-frame may start / end at most one IMU edge";
-            return VILBA_ERR_ARG;
-        }
-        if (bi >= 0) blk_edge_i[bi] = e;
-        if (bj >= 0) blk_edge_j[bj] = e;
-    }
-    const int n_pairs = n_free * (n_free + 1) / 2;
-    auto pair_index = [n_free](int a, int b) { return a * n_free - a * (a - 1) / 2 + (b - a); };
-    std::vector<int> pair_a(n_pairs), pair_b(n_pairs), blk_kf(n_free);
-    for (int a = 0; a < n_free; ++a)
-        for (int b = a; b < n_free; ++b) pair_a[pair_index(a, b)] = a, pair_b[pair_index(a, b)] = b;
-    for (int k = 0; k < K; ++k)
-        if (kf_block[k] >= 0) blk_kf[kf_block[k]] = k;
-    // the (edge_a, edge_b) lists themselves are built on the device (pairs.cu); capacity = sum m (m + 1) / 2
-    size_t n_triples = 0;
-    for (int p = 0; p < P; ++p) {
-        const size_t m = (size_t)(w->pt_obs_begin[p + 1] - w->pt_obs_begin[p]);
-        n_triples += m * (m + 1) / 2;
-    }
-    const int lin_ctas = ctx->dims.point_grid;
-    const Layout L = make_layout(K, NI, P, E, n, n_free, n_pairs, n_triples, lin_ctas);
-    CK(ctx->arena.reserve(L.total), "cudaMalloc(arena)");
-    CK(ctx->pinned.reserve(L.input_end), "cudaMallocHost(staging)");
-    char* h = ctx->pinned.base;
+// launch geometry of a batch: the per-window grids shrink as the batch grows so that one launch is about
+// one resident wave (2 CTAs of the per-point kernels per SM) whatever the number of windows
+LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni) {
+    LaunchDims d = ctx->dims;
+    const int sm = ctx->sm_count;
+    d.sm_count = sm;
+    d.n_windows = n_win;
+    d.point_grid = std::max(4, kPointGridPerSM * sm / n_win);
+    d.imu_grid = n_win == 1 ? kImuGrid : std::max(1, std::min(kImuGrid, max_ni));
+    d.gather_grid = std::max(2, 2 * sm / n_win);
+    d.reduce_grid = std::max(2, sm / n_win);
+    d.assemble_grid = std::max(4, 8 * sm / n_win);
+    d.chol_cluster = ctx->chol_cluster;
+    return d;
+}
+
+void drop_graphs(vilba_ctx* ctx) {
+    for (GraphEntry& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
+// flatten one window into its slice of the pinned staging buffer (phase A/B of the reference function:
+// gather + graph build, Optimizer.cpp:2329-2639, become "pack + one H2D")
+void pack_window(const vilba_window* w, const WinMeta& m, char* h) {
+    const Layout& L = m.L;
+    const int K = m.K, NI = m.NI, P = m.P, E = m.E, n_free = m.n_free, n_pairs = m.n_pairs;
     std::memcpy(h + L.kf_state0, w->kf_state, sizeof(double) * 22 * (size_t)K);
     if (P) std::memcpy(h + L.pts0, w->pt_xyz, sizeof(double) * 3 * (size_t)P);
     if (NI) std::memcpy(h + L.imu_preint, w->imu_preint, sizeof(double) * 142 * (size_t)NI);
@@ -305,72 +310,95 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     }
     if (P) std::memcpy(h + L.pt_obs_begin, w->pt_obs_begin, sizeof(int) * ((size_t)P + 1));
     else std::memset(h + L.pt_obs_begin, 0, sizeof(int));
-    std::memcpy(h + L.kf_block, kf_block.data(), sizeof(int) * (size_t)K);
+    int* kf_block = reinterpret_cast<int*>(h + L.kf_block);
+    int* blk_kf = reinterpret_cast<int*>(h + L.blk_kf);
+    int nf = 0;
+    for (int k = 0; k < K; ++k) {
+        kf_block[k] = (w->kf_flags[k] & VILBA_KF_FIXED) ? -1 : nf++;
+        if (kf_block[k] >= 0) blk_kf[kf_block[k]] = k;
+    }
     if (NI) {
         std::memcpy(h + L.imu_i, w->imu_kf_i, sizeof(int) * (size_t)NI);
         std::memcpy(h + L.imu_j, w->imu_kf_j, sizeof(int) * (size_t)NI);
     }
-    std::memcpy(h + L.blk_edge_i, blk_edge_i.data(), sizeof(int) * (size_t)n_free);
-    std::memcpy(h + L.blk_edge_j, blk_edge_j.data(), sizeof(int) * (size_t)n_free);
-    std::memcpy(h + L.blk_kf, blk_kf.data(), sizeof(int) * (size_t)n_free);
-    std::memcpy(h + L.pair_a, pair_a.data(), sizeof(int) * (size_t)n_pairs);
-    std::memcpy(h + L.pair_b, pair_b.data(), sizeof(int) * (size_t)n_pairs);
-    char* d = ctx->arena.base;
-    const auto t_packed = std::chrono::steady_clock::now();
-    CK(cudaMemcpyAsync(d, h, L.input_end, cudaMemcpyHostToDevice, ctx->stream), "H2D window");
-    if (std::getenv("VILBA_DEBUG_COUNTERS"))
-        std::fprintf(stderr, "[vilba dbg] flatten+pair lists %.3f ms, %zu bytes H2D, %zu list entries\n",
-                     std::chrono::duration<double, std::milli>(t_packed - t_begin).count(), L.input_end, n_triples);
-
-    DevWindow& dw = ctx->dw;
-    std::memset(&dw, 0, sizeof(dw));
-    dw.K = K, dw.NI = NI, dw.P = P, dw.E = E, dw.n_free = n_free, dw.n = n;
-    dw.lds = (n + 3) & ~3;
-    for (int b = 0; b < 2; ++b) {
-        dw.kf_state[b] = reinterpret_cast<double*>(d + L.kf_state[b]);
-        dw.pts[b] = reinterpret_cast<double*>(d + L.pts[b]);
+    // IMU edge of every block (as key-frame i / as key-frame j) and the key-frame block pairs (a <= b)
+    int* blk_edge_i = reinterpret_cast<int*>(h + L.blk_edge_i);
+    int* blk_edge_j = reinterpret_cast<int*>(h + L.blk_edge_j);
+    for (int b = 0; b < n_free; ++b) blk_edge_i[b] = blk_edge_j[b] = -1;
+    for (int e = 0; e < NI; ++e) {
+        const int bi = kf_block[w->imu_kf_i[e]], bj = kf_block[w->imu_kf_j[e]];
+        if (bi >= 0) blk_edge_i[bi] = e;
+        if (bj >= 0) blk_edge_j[bj] = e;
     }
-    dw.kf_block = reinterpret_cast<const int*>(d + L.kf_block);
-    dw.imu_i = reinterpret_cast<const int*>(d + L.imu_i);
-    dw.imu_j = reinterpret_cast<const int*>(d + L.imu_j);
-    dw.imu_preint = reinterpret_cast<const double*>(d + L.imu_preint);
-    dw.imu_info = reinterpret_cast<double*>(d + L.imu_info);
-    dw.imu_err = reinterpret_cast<double*>(d + L.imu_err);
-    dw.pt_obs_begin = reinterpret_cast<const int*>(d + L.pt_obs_begin);
-    dw.obs = reinterpret_cast<int4*>(d + L.obs);
-    dw.obs_chi2 = reinterpret_cast<double*>(d + L.obs_chi2);
-    dw.Hpp = reinterpret_cast<double*>(d + L.Hpp);
-    dw.bp = reinterpret_cast<double*>(d + L.bp);
-    dw.Hll = reinterpret_cast<double*>(d + L.Hll);
-    dw.bl = reinterpret_cast<double*>(d + L.bl);
-    dw.W = reinterpret_cast<double*>(d + L.W);
-    dw.lin_partial = reinterpret_cast<double*>(d + L.lin_partial);
-    dw.imu_slot = reinterpret_cast<double*>(d + L.imu_slot);
-    dw.mono_sum = reinterpret_cast<double*>(d + L.mono_sum);
-    dw.Y = reinterpret_cast<double*>(d + L.Y);
-    dw.blk_edge_i = reinterpret_cast<const int*>(d + L.blk_edge_i);
-    dw.blk_edge_j = reinterpret_cast<const int*>(d + L.blk_edge_j);
-    dw.edge_pt = reinterpret_cast<const int*>(d + L.edge_pt);
-    dw.n_pairs = n_pairs;
-    dw.pair_a = reinterpret_cast<const int*>(d + L.pair_a);
-    dw.pair_b = reinterpret_cast<const int*>(d + L.pair_b);
-    dw.pair_begin = reinterpret_cast<const int*>(d + L.pair_begin);
-    dw.pair_ea = reinterpret_cast<const int*>(d + L.pair_ea);
-    dw.pair_eb = reinterpret_cast<const int*>(d + L.pair_eb);
-    dw.blk_kf = reinterpret_cast<const int*>(d + L.blk_kf);
-    dw.edge_pt_rw = reinterpret_cast<int*>(d + L.edge_pt);
-    dw.pair_begin_rw = reinterpret_cast<int*>(d + L.pair_begin);
-    dw.pair_ea_rw = reinterpret_cast<int*>(d + L.pair_ea);
-    dw.pair_eb_rw = reinterpret_cast<int*>(d + L.pair_eb);
-    dw.pt_mask = reinterpret_cast<unsigned long long*>(d + L.pt_mask);
-    dw.S = reinterpret_cast<double*>(d + L.S);
-    dw.Lfac = reinterpret_cast<double*>(d + L.Lfac);
-    dw.cminv = reinterpret_cast<double*>(d + L.cminv);
-    dw.cdinv = reinterpret_cast<double*>(d + L.cdinv);
-    dw.bs = reinterpret_cast<double*>(d + L.bs);
-    dw.x = reinterpret_cast<double*>(d + L.x);
-    dw.lm = reinterpret_cast<LmState*>(d + L.lm);
-    dw.dbg = reinterpret_cast<long long*>(d + L.dbg);
+    int* pair_a = reinterpret_cast<int*>(h + L.pair_a);
+    int* pair_b = reinterpret_cast<int*>(h + L.pair_b);
+    int t = 0;
+    for (int a = 0; a < n_free; ++a)
+        for (int b = a; b < n_free; ++b, ++t) pair_a[t] = a, pair_b[t] = b;
+    (void)n_pairs;
+}
+
+void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta& m, char* d, LmState* lm, DevWindow& dw) {
+    const Layout& L = m.L;
+    char* in = d + m.in_base;
+    char* out = d + m.out_base;
+    char* wk = d + m.wk_base;
+    std::memset(&dw, 0, sizeof(dw));
+    dw.K = m.K, dw.NI = m.NI, dw.P = m.P, dw.E = m.E, dw.n_free = m.n_free, dw.n = m.n;
+    dw.lds = (m.n + 3) & ~3;
+    for (int b = 0; b < 2; ++b) {
+        dw.kf_state[b] = reinterpret_cast<double*>(wk + L.kf_state[b]);
+        dw.pts[b] = reinterpret_cast<double*>(wk + L.pts[b]);
+    }
+    dw.kf_state0 = reinterpret_cast<const double*>(in + L.kf_state0);
+    dw.pts0 = reinterpret_cast<const double*>(in + L.pts0);
+    dw.obs0 = reinterpret_cast<const int4*>(in + L.obs0);
+    dw.outlier = reinterpret_cast<uint8_t*>(wk + L.outlier);
+    dw.out_kf_state = reinterpret_cast<double*>(out + L.o_kf);
+    dw.out_pts = reinterpret_cast<double*>(out + L.o_pts);
+    dw.out_chi2 = reinterpret_cast<double*>(out + L.o_chi2);
+    dw.out_outlier = reinterpret_cast<uint8_t*>(out + L.o_outlier);
+    dw.kf_block = reinterpret_cast<const int*>(in + L.kf_block);
+    dw.imu_i = reinterpret_cast<const int*>(in + L.imu_i);
+    dw.imu_j = reinterpret_cast<const int*>(in + L.imu_j);
+    dw.imu_preint = reinterpret_cast<const double*>(in + L.imu_preint);
+    dw.imu_info = reinterpret_cast<double*>(wk + L.imu_info);
+    dw.imu_err = reinterpret_cast<double*>(wk + L.imu_err);
+    dw.pt_obs_begin = reinterpret_cast<const int*>(in + L.pt_obs_begin);
+    dw.obs = reinterpret_cast<int4*>(wk + L.obs);
+    dw.obs_chi2 = reinterpret_cast<double*>(wk + L.obs_chi2);
+    dw.Hpp = reinterpret_cast<double*>(wk + L.Hpp);
+    dw.bp = reinterpret_cast<double*>(wk + L.bp);
+    dw.Hll = reinterpret_cast<double*>(wk + L.Hll);
+    dw.bl = reinterpret_cast<double*>(wk + L.bl);
+    dw.W = reinterpret_cast<double*>(wk + L.W);
+    dw.lin_partial = reinterpret_cast<double*>(wk + L.lin_partial);
+    dw.imu_slot = reinterpret_cast<double*>(wk + L.imu_slot);
+    dw.mono_sum = reinterpret_cast<double*>(wk + L.mono_sum);
+    dw.Y = reinterpret_cast<double*>(wk + L.Y);
+    dw.blk_edge_i = reinterpret_cast<const int*>(in + L.blk_edge_i);
+    dw.blk_edge_j = reinterpret_cast<const int*>(in + L.blk_edge_j);
+    dw.edge_pt = reinterpret_cast<const int*>(wk + L.edge_pt);
+    dw.n_pairs = m.n_pairs;
+    dw.pair_a = reinterpret_cast<const int*>(in + L.pair_a);
+    dw.pair_b = reinterpret_cast<const int*>(in + L.pair_b);
+    dw.pair_begin = reinterpret_cast<const int*>(wk + L.pair_begin);
+    dw.pair_ea = reinterpret_cast<const int*>(wk + L.pair_ea);
+    dw.pair_eb = reinterpret_cast<const int*>(wk + L.pair_eb);
+    dw.blk_kf = reinterpret_cast<const int*>(in + L.blk_kf);
+    dw.edge_pt_rw = reinterpret_cast<int*>(wk + L.edge_pt);
+    dw.pair_begin_rw = reinterpret_cast<int*>(wk + L.pair_begin);
+    dw.pair_ea_rw = reinterpret_cast<int*>(wk + L.pair_ea);
+    dw.pair_eb_rw = reinterpret_cast<int*>(wk + L.pair_eb);
+    dw.pt_mask = reinterpret_cast<unsigned long long*>(wk + L.pt_mask);
+    dw.S = reinterpret_cast<double*>(wk + L.S);
+    dw.Lfac = reinterpret_cast<double*>(wk + L.Lfac);
+    dw.cminv = reinterpret_cast<double*>(wk + L.cminv);
+    dw.cdinv = reinterpret_cast<double*>(wk + L.cdinv);
+    dw.bs = reinterpret_cast<double*>(wk + L.bs);
+    dw.x = reinterpret_cast<double*>(wk + L.x);
+    dw.lm = lm;
+    dw.dbg = reinterpret_cast<long long*>(wk + L.dbg);
     if (const char* e = std::getenv("VILBA_CHOL_ABLATE")) dw.dbg_flags = std::atoi(e);
     dw.fx = w->fx, dw.fy = w->fy, dw.cx = w->cx, dw.cy = w->cy;
     for (int r = 0; r < 3; ++r)
@@ -387,13 +415,79 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
     dw.inv_gyr_rw2 = 1.0 / p.gyr_bias_rw2, dw.inv_acc_rw2 = 1.0 / p.acc_bias_rw2;
     dw.lm_tau = p.lm_tau, dw.lm_good_lo = p.lm_good_lo, dw.lm_good_hi = p.lm_good_hi;
     dw.max_trials = p.max_trials;
+}
 
-    ctx->L = L;
-    ctx->win_E = E, ctx->win_NI = NI, ctx->win_P = P, ctx->win_K = K;
-    // shared-memory capacities (and the captured graph) grow monotonically
-    if (K > ctx->cap_K || n_free > ctx->cap_nf || n > ctx->cap_n) {
-        ctx->cap_K = std::max(ctx->cap_K, (K + 31) / 32 * 32);
-        ctx->cap_nf = std::max(ctx->cap_nf, (n_free + 7) / 8 * 8);
+template <class F>
+void parallel_for(int n, int max_threads, F&& f) {
+    const int nt = std::max(1, std::min(n, max_threads));
+    if (nt == 1) {
+        for (int i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+            for (int i = t; i < n; i += nt) f(i);
+        });
+    for (auto& x : th) x.join();
+}
+
+// ------------------------------------------------------------------------------------------------
+// flatten + upload a batch of windows
+// ------------------------------------------------------------------------------------------------
+int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    ctx->n_win = 0;
+    if (n_win <= 0 || n_win > ctx->max_batch || !wins) {
+        ctx->err = "invalid batch size";
+        return VILBA_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    std::vector<WinMeta>& meta = ctx->meta;
+    meta.assign(n_win, WinMeta());
+    std::vector<int> status(n_win, VILBA_OK);
+    parallel_for(n_win, 8, [&](int i) {
+        const vilba_window* w = &wins[i];
+        int st = check_window(w);
+        if (st != VILBA_OK) {
+            status[i] = st;
+            return;
+        }
+        WinMeta& m = meta[i];
+        m.K = w->n_kf, m.NI = w->n_imu, m.P = w->n_pts, m.E = w->n_obs;
+        std::vector<int> kf_block(m.K, -1);
+        for (int k = 0; k < m.K; ++k)
+            if (!(w->kf_flags[k] & VILBA_KF_FIXED)) kf_block[k] = m.n_free++;
+        m.n = 15 * m.n_free;
+        m.n_pairs = m.n_free * (m.n_free + 1) / 2;
+        std::vector<char> is_i(m.n_free, 0), is_j(m.n_free, 0);
+        for (int e = 0; e < m.NI; ++e) {
+            const int bi = kf_block[w->imu_kf_i[e]], bj = kf_block[w->imu_kf_j[e]];
+            if ((bi >= 0 && is_i[bi]) || (bj >= 0 && is_j[bj]) || (bi >= 0 && bi == bj)) {
+                status[i] = VILBA_ERR_ARG - 100;  // a key-frame may start / end at most one IMU edge
+                return;
+            }
+            if (bi >= 0) is_i[bi] = 1;
+            if (bj >= 0) is_j[bj] = 1;
+        }
+        // the (edge_a, edge_b) lists of the Schur gather are built on the device (pairs.cu); capacity = sum m (m + 1) / 2
+        for (int p = 0; p < m.P; ++p) {
+            const size_t mm = (size_t)(w->pt_obs_begin[p + 1] - w->pt_obs_begin[p]);
+            m.n_triples += mm * (mm + 1) / 2;
+        }
+    });
+    int max_K = 0, max_nf = 0, max_ni = 0;
+    for (int i = 0; i < n_win; ++i) {
+        if (status[i] != VILBA_OK) {
+            ctx->err = status[i] == VILBA_ERR_ARG - 100 ? "a key-frame may start / end at most one IMU edge" : "invalid window";
+            return VILBA_ERR_ARG;
+        }
+        max_K = std::max(max_K, meta[i].K), max_nf = std::max(max_nf, meta[i].n_free), max_ni = std::max(max_ni, meta[i].NI);
+    }
+    // shared-memory capacities grow monotonically; the captured graphs depend on them
+    if (max_K > ctx->cap_K || max_nf > ctx->cap_nf) {
+        ctx->cap_K = std::max(ctx->cap_K, (max_K + 31) / 32 * 32);
+        ctx->cap_nf = std::max(ctx->cap_nf, (max_nf + 7) / 8 * 8);
         ctx->cap_n = std::max(ctx->cap_n, 15 * ctx->cap_nf);
         ctx->dims.smem_point = point_smem_bytes(ctx->cap_K);
         ctx->dims.smem_lin = linearize_smem_bytes(ctx->cap_K, ctx->cap_nf);
@@ -404,212 +498,251 @@ int upload_window(vilba_ctx* ctx, const vilba_window* w) {
             ctx->err = "window too large for the shared-memory stages";
             return VILBA_ERR_ARG;
         }
+        ctx->dims.chol_cluster = ctx->chol_cluster;
         CK(configure_kernels(ctx->dims), "cudaFuncSetAttribute");
-        if (ctx->slot_graph) {
-            cudaGraphExecDestroy(ctx->slot_graph);
-            ctx->slot_graph = nullptr;
-        }
+        drop_graphs(ctx);
     }
-    dw.chol_stage = chol_has_stage(ctx->cap_n) ? 1 : 0;
-    // device copy of the descriptor (staged behind the inputs in the pinned buffer)
-    CK(ctx->pinned_small.reserve(sizeof(DevWindow) + sizeof(LmState) + 256), "cudaMallocHost(desc)");
-    std::memcpy(ctx->pinned_small.base, &dw, sizeof(DevWindow));
-    CK(cudaMemcpyAsync(ctx->dwp, ctx->pinned_small.base, sizeof(DevWindow), cudaMemcpyHostToDevice, ctx->stream),
-       "H2D descriptor");
-    // the list builder reads the working copy of the observation table
-    if (E)
-        CK(cudaMemcpyAsync(d + L.obs, d + L.obs0, sizeof(int4) * (size_t)E, cudaMemcpyDeviceToDevice, ctx->stream),
-           "obs copy");
-    CK(launch_build_pair_lists(ctx->stream, ctx->dwp, ctx->dims), "pair lists");
-    ctx->stats.kernel_launches += 4;
-    ctx->has_window = true;
-    return VILBA_OK;
-}
-
-// restart from the uploaded initial state (device-to-device)
-int reset_window(vilba_ctx* ctx) {
-    const Layout& L = ctx->L;
+    ctx->dims = choose_dims(ctx, n_win, max_ni);
+    // arena: [inputs of all windows | outputs of all windows | LmState array | work regions]
+    size_t in_o = 0, out_o = 0, wk_o = 0;
+    for (int i = 0; i < n_win; ++i) {
+        WinMeta& m = meta[i];
+        m.L = make_layout(m, ctx->dims.point_grid);
+        m.in_base = in_o, in_o += m.L.in_bytes;
+        m.out_base = out_o, out_o += m.L.out_bytes;
+        m.wk_base = wk_o, wk_o += m.L.wk_bytes;
+    }
+    const size_t lm_bytes = align_up(sizeof(LmState) * (size_t)n_win);
+    ctx->in_total = in_o, ctx->out_total = out_o;
+    ctx->out_region = in_o;
+    ctx->lm_base = in_o + out_o;
+    const size_t wk_region = ctx->lm_base + lm_bytes;
+    for (int i = 0; i < n_win; ++i) meta[i].out_base += ctx->out_region, meta[i].wk_base += wk_region;
+    CK(ctx->arena.reserve(wk_region + wk_o), "cudaMalloc(arena)");
+    CK(ctx->pinned.reserve(in_o), "cudaMallocHost(staging)");
+    CK(ctx->pinned_out.reserve(out_o + lm_bytes), "cudaMallocHost(results)");
+    CK(ctx->pinned_small.reserve(sizeof(DevWindow) * (size_t)n_win + 256), "cudaMallocHost(desc)");
+    char* h = ctx->pinned.base;
     char* d = ctx->arena.base;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(d + L.kf_state[0], d + L.kf_state0, sizeof(double) * 22 * (size_t)ctx->win_K,
-                       cudaMemcpyDeviceToDevice, s), "reset kf");
-    CK(cudaMemcpyAsync(d + L.kf_state[1], d + L.kf_state0, sizeof(double) * 22 * (size_t)ctx->win_K,
-                       cudaMemcpyDeviceToDevice, s), "reset kf");
-    if (ctx->win_P) {
-        CK(cudaMemcpyAsync(d + L.pts[0], d + L.pts0, sizeof(double) * 3 * (size_t)ctx->win_P,
-                           cudaMemcpyDeviceToDevice, s), "reset pts");
-        CK(cudaMemcpyAsync(d + L.pts[1], d + L.pts0, sizeof(double) * 3 * (size_t)ctx->win_P,
-                           cudaMemcpyDeviceToDevice, s), "reset pts");
+    parallel_for(n_win, 8, [&](int i) { pack_window(&wins[i], meta[i], h + meta[i].in_base); });
+    const auto t_packed = std::chrono::steady_clock::now();
+    CK(cudaMemcpyAsync(d, h, in_o, cudaMemcpyHostToDevice, ctx->stream), "H2D windows");
+    if (std::getenv("VILBA_DEBUG_COUNTERS"))
+        std::fprintf(stderr, "[vilba dbg] flatten %d windows %.3f ms, %zu bytes H2D\n", n_win,
+                     std::chrono::duration<double, std::milli>(t_packed - t_begin).count(), in_o);
+    ctx->dw.resize(n_win);
+    LmState* lm0 = reinterpret_cast<LmState*>(d + ctx->lm_base);
+    for (int i = 0; i < n_win; ++i) {
+        fill_dev_window(ctx, &wins[i], meta[i], d, lm0 + i, ctx->dw[i]);
+        ctx->dw[i].chol_stage = chol_has_stage(ctx->cap_n) ? 1 : 0;
     }
-    if (ctx->win_E) {
-        CK(cudaMemcpyAsync(d + L.obs, d + L.obs0, sizeof(int4) * (size_t)ctx->win_E, cudaMemcpyDeviceToDevice, s),
-           "reset obs");
-        CK(cudaMemsetAsync(d + L.obs_chi2, 0, sizeof(double) * (size_t)ctx->win_E, s), "reset chi2");
-    }
-    CK(cudaMemsetAsync(d + L.lm, 0, sizeof(LmState), s), "reset lm");
-    if (std::getenv("VILBA_DEBUG_COUNTERS") && ctx->stats.solve_launches > 0) {
-        std::fprintf(stderr, "[vilba dbg] per launch: linearize_v2 %.1f us, schur_prep %.1f us, update_eval %.1f us\n",
-                     1e3 * ctx->dbg_ms[0] / std::max<long long>(1, ctx->stats.linearize_launches),
-                     1e3 * ctx->dbg_ms[1] / ctx->stats.solve_launches, 1e3 * ctx->dbg_ms[2] / ctx->stats.solve_launches);
-    }
-    if (std::getenv("VILBA_DEBUG_COUNTERS")) {
-        long long h[16];
-        if (cudaMemcpy(h, d + L.dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[8] > 0) {
-            std::fprintf(stderr, "[vilba dbg] chol calls=%lld avg cycles/phase:", h[8]);
-            for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %lld", h[i] / h[8]);
-            std::fprintf(stderr, "\n");
-        }
-        CK(cudaMemsetAsync(d + L.dbg, 0, sizeof(long long) * 16, s), "reset dbg");
-    }
+    std::memcpy(ctx->pinned_small.base, ctx->dw.data(), sizeof(DevWindow) * (size_t)n_win);
+    CK(cudaMemcpyAsync(ctx->dwp, ctx->pinned_small.base, sizeof(DevWindow) * (size_t)n_win, cudaMemcpyHostToDevice,
+                       ctx->stream), "H2D descriptors");
+    // working copies of the estimates / observation table, then the Schur pair lists (they read the table)
+    CK(launch_reset(ctx->stream, ctx->dwp, ctx->dims), "reset");
+    CK(launch_build_pair_lists(ctx->stream, ctx->dwp, ctx->dims), "pair lists");
+    ctx->stats.kernel_launches += 5;
+    ctx->n_win = n_win;
     return VILBA_OK;
 }
 
-// D2H of the controller state; waits for the stream while polling the caller's stop flag
-int read_lm(vilba_ctx* ctx, LmState* out, const volatile uint8_t* stop_flag) {
-    char* hp = ctx->pinned_small.base + sizeof(DevWindow) + 64;
-    CK(cudaMemcpyAsync(hp, ctx->dw.lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream), "D2H lm");
+// D2H of the controller states; waits for the stream while polling the caller's stop flag
+int read_lm(vilba_ctx* ctx, std::vector<LmState>& lm, const volatile uint8_t* stop_flag) {
+    char* hp = ctx->pinned_out.base + ctx->out_total;
+    const size_t bytes = sizeof(LmState) * (size_t)ctx->n_win;
+    CK(cudaMemcpyAsync(hp, ctx->arena.base + ctx->lm_base, bytes, cudaMemcpyDeviceToHost, ctx->stream), "D2H lm");
     if (stop_flag) {
         bool sent = false;
         while (cudaStreamQuery(ctx->stream) == cudaErrorNotReady) {
             if (!sent && *stop_flag) {  // mirror of `bool* pbStopFlag` (sparse_optimizer.h:188)
                 static const int one = 1;
-                cudaMemcpyAsync(&ctx->dw.lm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream2);
+                for (int i = 0; i < ctx->n_win; ++i)
+                    cudaMemcpyAsync(&ctx->dw[i].lm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream2);
                 sent = true;
             }
         }
     }
     CK(cudaStreamSynchronize(ctx->stream), "sync");
-    std::memcpy(out, hp, sizeof(LmState));
+    lm.resize(ctx->n_win);
+    std::memcpy(lm.data(), hp, bytes);
     probe_drain(ctx);
     return VILBA_OK;
 }
 
 bool stop_requested(const volatile uint8_t* f) { return f && *f; }
 
-int ensure_graph(vilba_ctx* ctx) {
-    if (!ctx->use_graph || ctx->slot_graph) return VILBA_OK;
+int ensure_graph(vilba_ctx* ctx, cudaGraphExec_t* out) {
+    for (const GraphEntry& g : ctx->graphs)
+        if (std::memcmp(&g.dims, &ctx->dims, sizeof(LaunchDims)) == 0) {
+            *out = g.exec;
+            return VILBA_OK;
+        }
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
     cudaError_t e = launch_slot(ctx->stream, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, nullptr);
     cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &g);
     if (fail(ctx, e, "capture slot") || fail(ctx, e2, "end capture")) return VILBA_ERR_CUDA;
-    e = cudaGraphInstantiate(&ctx->slot_graph, g, 0);
+    GraphEntry ge;
+    std::memset(&ge, 0, sizeof(ge));
+    ge.dims = ctx->dims;
+    e = cudaGraphInstantiate(&ge.exec, g, 0);
     cudaGraphDestroy(g);
     if (fail(ctx, e, "graph instantiate")) return VILBA_ERR_CUDA;
+    ctx->graphs.push_back(ge);
+    *out = ge.exec;
     return VILBA_OK;
 }
 
 // SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg (sparse_optimizer.cpp:354-419).
 // The loop itself runs on the device: the host enqueues slots (CUDA graph launches) without
-// synchronising and looks at the controller state once they have drained.
+// synchronising and looks at the controller states once they have drained.
 int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, const volatile uint8_t* stop_flag,
-              LmState* lm) {
+              std::vector<LmState>& lm) {
     cudaStream_t s = ctx->stream;
     vilba_stats& stt = ctx->stats;
     // computeActiveErrors + activeRobustChi2 at the first iteration; later iterations inherit currentChi
     // of the accepted trial (identical by construction: the errors are those of the accepted state)
     CK(launch_eval_initial(s, ctx->dwp, ctx->dims), "eval");
-    CK(launch_stage_begin(s, ctx->dwp, stage, iterations), "stage_begin");
+    CK(launch_stage_begin(s, ctx->dwp, ctx->dims, stage, iterations), "stage_begin");
     stt.kernel_launches += 2;
     const bool graph = ctx->use_graph && !ctx->profiling;
+    cudaGraphExec_t exec = nullptr;
     if (graph) {
-        int r = ensure_graph(ctx);
+        int r = ensure_graph(ctx, &exec);
         if (r != VILBA_OK) return r;
     }
-    const int first_trace = lm->n_trace;
-    int slots = iterations + 1;  // one trial per iteration when every step is accepted, plus one spare
+    std::vector<int> first_trace(ctx->n_win);
+    for (int i = 0; i < ctx->n_win; ++i) first_trace[i] = lm[i].n_trace;
+    // one trial per iteration when every step is accepted, plus spares for rejected trials
+    int slots = iterations + (ctx->n_win > 1 ? 3 : 1);
     for (int round = 0; round < 64; ++round) {
         for (int i = 0; i < slots; ++i) {
             if (graph)
-                CK(cudaGraphLaunch(ctx->slot_graph, s), "graph launch");
+                CK(cudaGraphLaunch(exec, s), "graph launch");
             else
                 CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, probe_take(ctx)), "slot");
             stt.kernel_launches += kKernelsPerSlot;
         }
         int r = read_lm(ctx, lm, stop_flag);
         if (r != VILBA_OK) return r;
-        if (lm->phase == PH_DONE) break;
+        bool done = true;
+        for (int i = 0; i < ctx->n_win; ++i) done = done && lm[i].phase == PH_DONE;
+        if (done) break;
         slots = 2;  // rejected trials used up the slack: keep going
     }
-    for (int i = first_trace; i < lm->n_trace && out->n_trace < VILBA_MAX_TRACE; ++i) {
-        const IterRec& t = lm->trace[i];
-        vilba_iter_record& rec = out->trace[out->n_trace++];
-        rec.stage = t.stage, rec.iteration = t.iteration, rec.trials = t.trials, rec.result = t.result;
-        rec.n_active_edges = t.n_active, rec.accepted = t.accepted;
-        rec.chi2_initial = t.chi0, rec.chi2_final = t.chi1, rec.lambda = t.lambda, rec.lambda_first_trial = t.lambda_first;
-        stt.lm_iterations++;
-        stt.lm_trials += t.trials;
-        stt.edges_linearized += t.n_active;
+    for (int wdx = 0; wdx < ctx->n_win; ++wdx) {
+        vilba_result& o = out[wdx];
+        for (int i = first_trace[wdx]; i < lm[wdx].n_trace && o.n_trace < VILBA_MAX_TRACE; ++i) {
+            const IterRec& t = lm[wdx].trace[i];
+            vilba_iter_record& rec = o.trace[o.n_trace++];
+            rec.stage = t.stage, rec.iteration = t.iteration, rec.trials = t.trials, rec.result = t.result;
+            rec.n_active_edges = t.n_active, rec.accepted = t.accepted;
+            rec.chi2_initial = t.chi0, rec.chi2_final = t.chi1, rec.lambda = t.lambda, rec.lambda_first_trial = t.lambda_first;
+            stt.lm_iterations++;
+            stt.lm_trials += t.trials;
+            stt.edges_linearized += t.n_active;
+        }
     }
     return VILBA_OK;
 }
 
-int solve_resident(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_flag) {
-    if (!ctx->has_window) {
+void debug_counters(vilba_ctx* ctx) {
+    if (!std::getenv("VILBA_DEBUG_COUNTERS") || ctx->n_win < 1) return;
+    if (ctx->stats.solve_launches > 0)
+        std::fprintf(stderr, "[vilba dbg] per launch: linearize_v2 %.1f us, schur_prep %.1f us, update_eval %.1f us\n",
+                     1e3 * ctx->dbg_ms[0] / std::max<long long>(1, ctx->stats.linearize_launches),
+                     1e3 * ctx->dbg_ms[1] / ctx->stats.solve_launches, 1e3 * ctx->dbg_ms[2] / ctx->stats.solve_launches);
+    long long h[16];
+    if (cudaMemcpy(h, ctx->dw[0].dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[8] > 0) {
+        std::fprintf(stderr, "[vilba dbg] chol calls=%lld avg cycles/phase:", h[8]);
+        for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %lld", h[i] / h[8]);
+        std::fprintf(stderr, "\n");
+    }
+    cudaMemset(ctx->dw[0].dbg, 0, sizeof(long long) * 16);
+}
+
+// phases C..E for every window of the resident batch; out[i] receives status / trace / timing
+int solve_batch(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_flag) {
+    if (ctx->n_win <= 0) {
         ctx->err = "no window uploaded";
         return VILBA_ERR_ARG;
     }
-    out->n_trace = 0;
-    out->stage2_ran = 0;
-    out->n_outliers_stage1 = 0;
-    out->solve_ms = 0.0;
-    out->status = VILBA_OK;
+    const int nw = ctx->n_win;
+    for (int i = 0; i < nw; ++i) {
+        out[i].n_trace = 0;
+        out[i].stage2_ran = 0;
+        out[i].n_outliers_stage1 = 0;
+        out[i].solve_ms = 0.0;
+        out[i].status = VILBA_OK;
+    }
     if (stop_requested(stop_flag)) {  // Optimizer.cpp:2643-2645
-        out->status = VILBA_ABORTED;
+        for (int i = 0; i < nw; ++i) out[i].status = VILBA_ABORTED;
         return VILBA_ABORTED;
     }
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     cudaStream_t s = ctx->stream;
-    int r = reset_window(ctx);
-    if (r != VILBA_OK) return r;
+    debug_counters(ctx);
+    CK(launch_reset(s, ctx->dwp, ctx->dims), "reset");  // every solve restarts from the uploaded state
     CK(cudaEventRecord(ctx->ev_a, s), "event");
-    CK(launch_imu_prepare(s, ctx->dwp), "imu_prepare");
-    ctx->stats.kernel_launches += 1;
-    LmState lm;
-    std::memset(&lm, 0, sizeof(lm));
-    r = run_stage(ctx, 1, ctx->prm.iters_stage1, out, stop_flag, &lm);
+    CK(launch_imu_prepare(s, ctx->dwp, ctx->dims), "imu_prepare");
+    ctx->stats.kernel_launches += 2;
+    std::vector<LmState> lm(nw);
+    std::memset(lm.data(), 0, sizeof(LmState) * (size_t)nw);
+    int r = run_stage(ctx, 1, ctx->prm.iters_stage1, out, stop_flag, lm);
     if (r != VILBA_OK) return r;
-    if (!stop_requested(stop_flag) && !lm.stop) {  // bDoMore (Optimizer.cpp:2650-2656)
+    bool stopped = stop_requested(stop_flag);
+    for (int i = 0; i < nw; ++i) stopped = stopped || lm[i].stop;
+    if (!stopped) {  // bDoMore (Optimizer.cpp:2650-2656)
         CK(launch_cull(s, ctx->dwp, ctx->dims), "cull");
         ctx->stats.kernel_launches += 1;
-        r = run_stage(ctx, 2, ctx->prm.iters_stage2, out, stop_flag, &lm);
+        r = run_stage(ctx, 2, ctx->prm.iters_stage2, out, stop_flag, lm);
         if (r != VILBA_OK) return r;
-        out->n_outliers_stage1 = lm.n_culled;
-        out->stage2_ran = 1;
+        for (int i = 0; i < nw; ++i) {
+            out[i].n_outliers_stage1 = lm[i].n_culled;
+            out[i].stage2_ran = 1;
+        }
     }
-    uint8_t* outl = reinterpret_cast<uint8_t*>(ctx->arena.base + ctx->L.outlier);
-    CK(launch_final_flags(s, ctx->dwp, ctx->dims, outl), "final_flags");
+    CK(launch_final_flags(s, ctx->dwp, ctx->dims), "final_flags");
     ctx->stats.kernel_launches += 1;
     CK(cudaEventRecord(ctx->ev_b, s), "event");
     CK(cudaStreamSynchronize(s), "sync");
     probe_drain(ctx);
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b), "elapsed");
-    out->solve_ms = ms;
-    ctx->last_cur = lm.cur;
+    for (int i = 0; i < nw; ++i) out[i].solve_ms = ms;  // device time of the whole batch
     return VILBA_OK;
 }
 
-int download_window(vilba_ctx* ctx, vilba_result* out) {
-    if (!ctx->has_window) return VILBA_ERR_ARG;
-    struct { int cur; } lm = {ctx->last_cur};
-    const Layout& L = ctx->L;
-    char* d = ctx->arena.base;
+// pack the results of every window on the device, one D2H, scatter into the caller's arrays
+int download_batch(vilba_ctx* ctx, vilba_result* out) {
+    if (ctx->n_win <= 0) return VILBA_ERR_ARG;
     cudaStream_t s = ctx->stream;
-    if (out->kf_state)
-        CK(cudaMemcpyAsync(out->kf_state, d + L.kf_state[lm.cur], sizeof(double) * 22 * (size_t)ctx->win_K,
-                           cudaMemcpyDeviceToHost, s), "D2H kf");
-    if (out->pt_xyz && ctx->win_P)
-        CK(cudaMemcpyAsync(out->pt_xyz, d + L.pts[lm.cur], sizeof(double) * 3 * (size_t)ctx->win_P,
-                           cudaMemcpyDeviceToHost, s), "D2H pts");
-    if (out->obs_outlier && ctx->win_E)
-        CK(cudaMemcpyAsync(out->obs_outlier, d + L.outlier, (size_t)ctx->win_E, cudaMemcpyDeviceToHost, s),
-           "D2H outlier");
-    if (out->obs_chi2 && ctx->win_E)
-        CK(cudaMemcpyAsync(out->obs_chi2, d + L.obs_chi2, sizeof(double) * (size_t)ctx->win_E,
-                           cudaMemcpyDeviceToHost, s), "D2H chi2");
+    CK(launch_export(s, ctx->dwp, ctx->dims), "export");
+    ctx->stats.kernel_launches += 1;
+    char* hp = ctx->pinned_out.base;
+    CK(cudaMemcpyAsync(hp, ctx->arena.base + ctx->out_region, ctx->out_total, cudaMemcpyDeviceToHost, s), "D2H results");
     CK(cudaStreamSynchronize(s), "sync");
+    parallel_for(ctx->n_win, 8, [&](int i) {
+        const WinMeta& m = ctx->meta[i];
+        const char* src = hp + (m.out_base - ctx->out_region);
+        vilba_result& o = out[i];
+        if (o.kf_state) std::memcpy(o.kf_state, src + m.L.o_kf, sizeof(double) * 22 * (size_t)m.K);
+        if (o.pt_xyz && m.P) std::memcpy(o.pt_xyz, src + m.L.o_pts, sizeof(double) * 3 * (size_t)m.P);
+        if (o.obs_chi2 && m.E) std::memcpy(o.obs_chi2, src + m.L.o_chi2, sizeof(double) * (size_t)m.E);
+        if (o.obs_outlier && m.E) std::memcpy(o.obs_outlier, src + m.L.o_outlier, (size_t)m.E);
+    });
     return VILBA_OK;
+}
+
+void add_stats(vilba_stats& a, const vilba_stats& b) {
+    a.kernel_launches += b.kernel_launches;
+    a.lm_iterations += b.lm_iterations;
+    a.lm_trials += b.lm_trials;
+    a.edges_linearized += b.edges_linearized;
+    a.linearize_ms += b.linearize_ms, a.linearize_launches += b.linearize_launches;
+    a.schur_ms += b.schur_ms, a.schur_launches += b.schur_launches;
+    a.solve_ms += b.solve_ms, a.solve_launches += b.solve_launches;
 }
 
 }  // namespace
@@ -637,7 +770,9 @@ void vilba_default_params(vilba_params* p) {
     p->acc_meas_cov = 2.0e-3 * 2.0e-3 / 0.005 * 100;
 }
 
-const char* vilba_version(void) { return "vilba 0.1 (sm_100a, FP64)"; }
+const char* vilba_version(void) { return "vilba 0.2 (sm_100a, FP64)"; }
+
+int vilba_max_batch(void) { return kMaxBatch; }
 
 vilba_ctx* vilba_create(int device, const vilba_params* params) {
     int n_dev = 0;
@@ -656,15 +791,14 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    ctx->dims.sm_count = ctx->sm_count;
-    ctx->dims.point_grid = kPointGridPerSM * ctx->sm_count;
-    ctx->dims.chol_cluster = 8;
+    std::memset(&ctx->dims, 0, sizeof(ctx->dims));
     ctx->dims.chol_nb = 32;
-    ctx->dims.smem_point = ctx->dims.smem_lin = ctx->dims.smem_chol = 0;
-    if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->dims.chol_cluster = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("VILBA_BATCH_LANES")) ctx->n_lanes = std::max(1, std::atoi(e));
-    if (cudaMalloc(&ctx->dwp, sizeof(DevWindow)) != cudaSuccess) {
+    if (const char* e = std::getenv("VILBA_MAX_BATCH")) ctx->max_batch = std::max(1, std::min(kMaxBatch, std::atoi(e)));
+    ctx->dims = choose_dims(ctx, 1, 0);
+    if (cudaMalloc(&ctx->dwp, sizeof(DevWindow) * kMaxBatch) != cudaSuccess) {
         delete ctx;
         return nullptr;
     }
@@ -688,11 +822,12 @@ void vilba_destroy(vilba_ctx* ctx) {
     ctx->lanes.clear();
     cudaSetDevice(ctx->device);
     for (cudaEvent_t e : ctx->probes) cudaEventDestroy(e);
-    if (ctx->slot_graph) cudaGraphExecDestroy(ctx->slot_graph);
+    drop_graphs(ctx);
     if (ctx->dwp) cudaFree(ctx->dwp);
     ctx->arena.release();
     ctx->preint_arena.release();
     ctx->pinned.release();
+    ctx->pinned_out.release();
     ctx->pinned_small.release();
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -707,19 +842,40 @@ const char* vilba_last_error(const vilba_ctx* ctx) { return ctx ? ctx->err.c_str
 
 int vilba_window_upload(vilba_ctx* ctx, const vilba_window* win) {
     if (!ctx) return VILBA_ERR_ARG;
-    return upload_window(ctx, win);
+    return upload_batch(ctx, 1, win);
 }
 
 int vilba_window_solve_resident(vilba_ctx* ctx, vilba_result* out) {
     if (!ctx || !out) return VILBA_ERR_ARG;
-    int r = solve_resident(ctx, out, nullptr);
+    if (ctx->n_win != 1) {
+        ctx->err = "no single window uploaded";
+        return VILBA_ERR_ARG;
+    }
+    int r = solve_batch(ctx, out, nullptr);
     out->status = r;
     return r;
 }
 
 int vilba_window_download(vilba_ctx* ctx, vilba_result* out) {
-    if (!ctx || !out) return VILBA_ERR_ARG;
-    return download_window(ctx, out);
+    if (!ctx || !out || ctx->n_win != 1) return VILBA_ERR_ARG;
+    return download_batch(ctx, out);
+}
+
+int vilba_batch_upload(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win) {
+    if (!ctx) return VILBA_ERR_ARG;
+    return upload_batch(ctx, n_windows, win);
+}
+
+int vilba_batch_solve_resident(vilba_ctx* ctx, int32_t n_windows, vilba_result* out) {
+    if (!ctx || !out || n_windows != ctx->n_win) return VILBA_ERR_ARG;
+    int r = solve_batch(ctx, out, nullptr);
+    for (int i = 0; i < n_windows; ++i) out[i].status = r;
+    return r;
+}
+
+int vilba_batch_download(vilba_ctx* ctx, int32_t n_windows, vilba_result* out) {
+    if (!ctx || !out || n_windows != ctx->n_win) return VILBA_ERR_ARG;
+    return download_batch(ctx, out);
 }
 
 int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, const volatile uint8_t* stop_flag) {
@@ -732,45 +888,54 @@ int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, c
         out->status = VILBA_ABORTED;
         return VILBA_ABORTED;
     }
-    int r = upload_window(ctx, win);
-    if (r == VILBA_OK) r = solve_resident(ctx, out, stop_flag);
-    if (r == VILBA_OK) r = download_window(ctx, out);
+    int r = upload_batch(ctx, 1, win);
+    if (r == VILBA_OK) r = solve_batch(ctx, out, stop_flag);
+    if (r == VILBA_OK) r = download_batch(ctx, out);
     out->status = r;
     return r;
 }
 
-// Independent windows (BASELINE config 5): a pool of sub-contexts ("lanes"), each with its own streams, arena
-// and CUDA graph, driven by one host thread per lane.  A single window leaves most of the GPU idle during its
-// latency-bound phases (the 8-CTA Cholesky cluster above all), so concurrent windows fill the machine.
+// Independent windows (BASELINE config 5).  The windows are cut into chunks of up to kMaxBatch; every chunk is
+// ONE batched solve (each kernel launched once for all its windows), and the chunks are pipelined over a few
+// sub-contexts ("lanes", one host thread each) so that the flatten / H2D / D2H of one chunk overlaps the
+// solve of another.
 int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win, vilba_result* out) {
     if (!ctx || n_windows < 0 || (n_windows && (!win || !out))) return VILBA_ERR_ARG;
     if (n_windows == 0) return VILBA_OK;
-    const int lanes = std::max(1, std::min(ctx->n_lanes, (int)n_windows));
+    const int chunk = ctx->max_batch;
+    const int n_chunks = (n_windows + chunk - 1) / chunk;
+    auto run_chunk = [&](vilba_ctx* c, int ci) {
+        const int b = ci * chunk, nb = std::min(chunk, (int)n_windows - b);
+        int r = upload_batch(c, nb, win + b);
+        if (r == VILBA_OK) r = solve_batch(c, out + b, nullptr);
+        if (r == VILBA_OK) r = download_batch(c, out + b);
+        for (int i = 0; i < nb; ++i) out[b + i].status = r;
+        return r;
+    };
+    if (n_chunks == 1) return run_chunk(ctx, 0);
+    const int lanes = std::max(1, std::min(ctx->n_lanes, n_chunks));
     while ((int)ctx->lanes.size() < lanes) {
         vilba_ctx* sub = vilba_create(ctx->device, &ctx->prm);
         if (!sub) {
             ctx->err = "could not create a batch lane";
             return VILBA_ERR_CUDA;
         }
+        sub->max_batch = ctx->max_batch;
         ctx->lanes.push_back(sub);
     }
     std::vector<int> status(lanes, VILBA_OK);
     std::vector<std::thread> th;
     for (int l = 0; l < lanes; ++l)
         th.emplace_back([&, l]() {
-            for (int i = l; i < n_windows; i += lanes) {
-                const int r = vilba_local_ba(ctx->lanes[l], &win[i], &out[i], nullptr);
+            for (int ci = l; ci < n_chunks; ci += lanes) {
+                const int r = run_chunk(ctx->lanes[l], ci);
                 if (r < 0) status[l] = r;
             }
         });
     for (auto& t : th) t.join();
     int worst = VILBA_OK;
     for (int l = 0; l < lanes; ++l) {
-        const vilba_stats& s = ctx->lanes[l]->stats;
-        ctx->stats.kernel_launches += s.kernel_launches;
-        ctx->stats.lm_iterations += s.lm_iterations;
-        ctx->stats.lm_trials += s.lm_trials;
-        ctx->stats.edges_linearized += s.edges_linearized;
+        add_stats(ctx->stats, ctx->lanes[l]->stats);
         std::memset(&ctx->lanes[l]->stats, 0, sizeof(vilba_stats));
         if (status[l] < 0) {
             worst = status[l];

@@ -100,6 +100,39 @@ def test_batch_entry(ctx, oracle):
         _compare(r, oracle.local_ba(w), w)
 
 
+def test_batch_of_mixed_windows_in_one_launch(ctx, oracle):
+    """Windows of different sizes / fixed-key-frame counts / outlier rates solved by ONE batched launch per
+    kernel (grid row = window), each with its own device-side LM controller."""
+    wins = [synth.make_config("small", window_index=0),
+            synth.make_config("tiny", window_index=1),
+            synth.make_config("small", window_index=2, n_fixed_extra=2, outlier_frac=0.1),
+            synth.make_config("c1", window_index=3),
+            synth.make_config("tiny", window_index=4, outlier_frac=0.2)]
+    ctx.upload_batch(wins)
+    solved = ctx.solve_batch_resident()
+    again = ctx.solve_batch_resident()  # restarts from the uploaded state
+    down = ctx.download_batch()
+    for w, s, a, d in zip(wins, solved, again, down):
+        assert [t["trials"] for t in s.trace] == [t["trials"] for t in a.trace]
+        _compare(_merge(d, a), oracle.local_ba(w), w)
+    # the host-buffer entry point takes the same path
+    for w, r in zip(wins, ctx.local_ba_batch(wins)):
+        _compare(r, oracle.local_ba(w), w)
+
+
+def test_batch_larger_than_one_chunk(ctx, oracle, monkeypatch):
+    """More windows than one batched launch holds: chunks are pipelined over two lanes."""
+    monkeypatch.setenv("VILBA_MAX_BATCH", "3")
+    from mc_slam_b200 import api
+    c = api.Context(0)
+    try:
+        wins = [synth.make_config("tiny", window_index=i, outlier_frac=0.03 * i) for i in range(8)]
+        for w, r in zip(wins, c.local_ba_batch(wins)):
+            _compare(r, oracle.local_ba(w), w)
+    finally:
+        c.close()
+
+
 def test_invalid_window_is_rejected(ctx, vilba):
     w = synth.make_config("tiny")
     w.obs_kf = w.obs_kf.copy()

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Throughput of independent windows through vilba_local_ba_batch (BASELINE config 5 shape, scaled down):
-N copies of distinct C3-shaped windows, host buffers in, host buffers out."""
+"""Throughput of independent windows solved as ONE batched launch per kernel (BASELINE config 5 shape:
+64 C3 windows per GPU).  Prints the device time of the resident batch and the end-to-end time through
+vilba_local_ba_batch (host buffers in, host buffers out)."""
 import os
 import sys
 import time
@@ -8,15 +9,31 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mc_slam_b200 import api, synth  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 name = sys.argv[2] if len(sys.argv) > 2 else "c3"
-base = [synth.make_config(name, window_index=i) for i in range(min(n, 8))]
-wins = [base[i % len(base)] for i in range(n)]
+sizes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "32").split(",")]
+base = [synth.make_config(name, window_index=i) for i in range(min(max(sizes), 8))]
 ctx = api.Context(0)
-ctx.local_ba_batch(wins[: min(n, 8)])  # warm-up: lanes, graphs, arenas
-for lanes_note in (os.environ.get("VILBA_BATCH_LANES", "8"),):
+prof = os.environ.get("BATCH_PROFILE", "0") == "1"
+for n in sizes:
+    wins = [base[i % len(base)] for i in range(n)]
+    if n <= api.max_batch():
+        ctx.upload_batch(wins)
+        ctx.solve_batch_resident()
+        rs = ctx.solve_batch_resident()
+        iters = sum(len(r.trace) for r in rs)
+        ms = rs[0].solve_ms
+        print(f"resident batch n={n} {name}: {ms:.2f} ms device -> {iters/ms*1e3:.0f} LM iters/s, {n/ms*1e3:.1f} windows/s", flush=True)
+        if prof:
+            ctx.reset_stats()
+            ctx.set_profiling(True)
+            ctx.solve_batch_resident()
+            s = ctx.stats()
+            ctx.set_profiling(False)
+            print(f"   per launch: linearize {1e3*s.linearize_ms/max(1,s.linearize_launches):.1f} us x{s.linearize_launches}, "
+                  f"schur {1e3*s.schur_ms/max(1,s.schur_launches):.1f} us, chol {1e3*s.solve_ms/max(1,s.solve_launches):.1f} us x{s.solve_launches}", flush=True)
+    ctx.local_ba_batch(wins)  # warm-up: lanes, graphs, arenas
     t0 = time.perf_counter()
     rs = ctx.local_ba_batch(wins)
     dt = time.perf_counter() - t0
     iters = sum(len(r.trace) for r in rs)
-    print(f"lanes={lanes_note} windows={n} {name}: {dt*1e3:.1f} ms -> {n/dt:.1f} windows/s, {iters/dt:.0f} LM iters/s (e2e, host buffers)")
+    print(f"e2e batch n={n} {name}: {dt*1e3:.1f} ms -> {n/dt:.1f} windows/s, {iters/dt:.0f} LM iters/s (host buffers)", flush=True)
