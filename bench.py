@@ -2,17 +2,22 @@
 """bench.py -- headline benchmark of the VI local-BA hot path (BASELINE.json metric:
 "local-BA LM iters/sec + edges linearized/sec (20KF/5k pts), % HBM roofline").
 
-One "step" = one full pass of the path over one synthetic EuRoC-shaped window: phases C..E of
-Optimizer::LocalBundleAdjustmentNavState (5 robust + 10 non-robust LM iterations, cull, outlier flags).
+One "step" = one full pass of the path over one batch of synthetic EuRoC-shaped 20-KF / 5k-point windows
+(BASELINE config 5's per-GPU share: 512 windows over 8 GPUs = 64 independent windows per GPU, solved by ONE
+batched launch per kernel): phases C..E of Optimizer::LocalBundleAdjustmentNavState for every window
+(5 robust + 10 non-robust LM iterations, cull, outlier flags).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU)
     python bench.py --impl reference ...                     # the CPU restatement of the reference path
+    python bench.py --windows 1                              # latency of ONE window (BASELINE config 3)
 
-value   : LM outer iterations / s, window resident in HBM when the timed region starts (device time
-          from CUDA events on the library's stream, L2 flushed between steps, max over ranks)
-e2e     : same metric through the C-ABI call vilba_local_ba() with HOST buffers (H2D + solve + D2H)
-Multi-GPU: windows are independent (BASELINE config 5) -> each rank owns its own window, no
-          data-path collective, "weak" scaling; torch.distributed only carries the barrier/max.
+value   : LM outer iterations / s over all windows, windows resident in HBM when the timed region starts
+          (device time from CUDA events on the library's stream, L2 flushed between steps, max over ranks)
+e2e     : same metric through the C-ABI call vilba_local_ba_batch() with HOST buffers
+          (flatten + H2D + solve + D2H inside the timed region)
+single_window : the same two numbers for ONE 20-KF window (latency-bound; BASELINE config 3)
+Multi-GPU: windows are independent -> each rank owns its own batch, no data-path collective, "weak"
+          scaling; torch.distributed only carries the barrier/max.
 """
 from __future__ import annotations
 
@@ -30,7 +35,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_TRAFFIC_LINEARIZE = 8071168  # bytes/launch: dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_full_summary.txt
 METRIC = "local_ba_lm_iters_per_sec"
 UNIT = "LM iters/s"
 
@@ -95,9 +99,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_desc(w, name):
-    return (f"{name}: {w.n_kf} KF ({w.n_free} free) / {w.n_pts} pts / {w.n_obs} mono + {w.n_imu}+{w.n_imu} IMU edges, "
-            f"5+10 LM iters")
+def workload_desc(w, name, nw):
+    one = (f"{name}: {w.n_kf} KF ({w.n_free} free) / {w.n_pts} pts / {w.n_obs} mono + {w.n_imu}+{w.n_imu} IMU edges, "
+           f"5+10 LM iters")
+    return one if nw == 1 else f"{nw} independent windows per GPU in one batched launch (C5 share), each ~ {one}"
 
 
 def algorithmic_bytes_linearize(w):
@@ -109,47 +114,94 @@ def algorithmic_bytes_linearize(w):
     return w.n_obs * 20 + w.n_pts * 24 + e_free * 144 + w.n_pts * 96 + n * n * 4 + n * 8
 
 
+def ncu_traffic(kernel, nw, workload):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/ncu_traffic.json: {"<workload>x<windows>": {"<kernel>": bytes}}), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[f"{workload}x{nw}"][kernel]
+    except Exception:
+        return None
+
+
+def cpu_throughput(wins, threads, reps_per_thread):
+    """The CPU restatement of the reference path (oracle/, g++ -O3 -march=native) on `threads` host threads,
+    one window per thread at a time (g2o itself is single-threaded per optimisation: Thirdparty/g2o/config.h:4).
+    Returns (LM iters/s over the wall time of the sample, windows solved, iters, edges, wall seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    pyoracle.local_ba(wins[0])  # warm-up (library load, page-in)
+    jobs = [wins[i % len(wins)] for i in range(threads * reps_per_thread)]
+
+    def one(w):
+        r = pyoracle.local_ba(w)  # ctypes releases the GIL inside the C call
+        return len(r.trace), sum(t["n_active_edges"] for t in r.trace), r.solve_ms
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        out = [one(w) for w in jobs]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            out = list(ex.map(one, jobs))
+    wall = time.perf_counter() - t0
+    iters = sum(o[0] for o in out)
+    edges = sum(o[1] for o in out)
+    solve_s = sum(o[2] for o in out) * 1e-3
+    # single-thread figure: phases C..E only (CUDA-event equivalent); multi-thread: wall time of the sample
+    val = iters / solve_s if threads == 1 else iters / wall
+    return val, len(jobs), iters, edges, wall
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the dependency-free restatement of the reference's g2o path (the reference itself
-    cannot be compiled here: Eigen/OpenCV/CHOLMOD are absent).  Single-threaded like the reference
-    (g2o is built without OpenMP, Thirdparty/g2o/config.h:4; BA runs on the one LocalMapping thread)."""
+    """CPU arm: the dependency-free restatement of the reference's g2o path (the reference itself cannot be
+    compiled here: Eigen/OpenCV/CHOLMOD are absent), on all host threads the workload can use: one window
+    per thread (each optimisation is single-threaded like the reference's)."""
     if rank != 0:
         return
     from mc_slam_b200 import synth
-    from oracle import pyoracle
-    w = synth.make_config(args.workload)
-    for _ in range(max(1, min(args.warmup, 1))):
-        pyoracle.local_ba(w)
-    iters, ms, edges = 0, 0.0, 0
-    steps = max(1, min(args.steps, 5))  # bounded sample: one window solve is ~0.4 s on one core
-    for _ in range(steps):
-        r = pyoracle.local_ba(w)
-        iters += len(r.trace)
-        edges += sum(t["n_active_edges"] for t in r.trace)
-        ms += r.solve_ms
-    val = iters / (ms * 1e-3)
+    nw = args.windows
+    threads = 1 if nw == 1 else min(host_threads(), nw)
+    wins = [synth.make_config(args.workload, window_index=i) for i in range(min(nw, max(threads, 1)))]
+    steps = max(1, min(args.steps, 4))  # bounded sample: one window solve is ~0.3 s on one core
+    val, n_solved, iters, edges, wall = cpu_throughput(wins, threads, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": 1, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(w, args.workload), "threads": 1},
-        "edges_linearized_per_sec": edges / (ms * 1e-3),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{steps} full solves of the same {args.workload} window, oracle/libvilba_oracle.so, 1 thread"},
+        "config": {"workload": workload_desc(wins[0], args.workload, nw), "threads": threads},
+        "edges_linearized_per_sec": edges / wall if threads > 1 else None,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_solved} window solves ({steps} per thread) of the same workload, "
+                                   f"oracle/libvilba_oracle.so, {threads} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def window_bytes(w):
+    h2d = (w.kf_state.nbytes + w.pt_xyz.nbytes + w.imu_preint.nbytes + 16 * w.n_obs + w.pt_obs_begin.nbytes
+           + 4 * w.n_kf + 8 * w.n_imu)
+    d2h = w.kf_state.nbytes + w.pt_xyz.nbytes + w.n_obs + 8 * w.n_obs
+    return h2d, d2h
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c3", "c4", "small", "tiny"])
+    ap.add_argument("--windows", type=int, default=64, help="independent windows per GPU solved as one batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +231,10 @@ def main():
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
-    win = synth.make_config(args.workload, window_index=rank)  # every rank owns an independent window
+    nw = max(1, min(args.windows, api.max_batch()))
+    # every rank owns its own slice of the global list of independent windows (C5: window w uses seed + 1000 w)
+    w0, _ = sharding.shard_range(nw * world, rank, world)
+    wins = [synth.make_config(args.workload, window_index=w0 + i) for i in range(nw)]
     ctx = api.Context(local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -187,56 +242,76 @@ def main():
         flush.fill_(1)
         torch.cuda.synchronize()
 
+    def timed_resident(c, k):
+        ms, iters, edges = 0.0, 0, 0
+        for _ in range(k):
+            flush_l2()
+            rs = c.solve_batch_resident()
+            ms += rs[0].solve_ms  # device time of the whole batch
+            iters += sum(len(r.trace) for r in rs)
+            edges += sum(t["n_active_edges"] for r in rs for t in r.trace)
+        return ms, iters, edges
+
     # ---- HBM-resident timing --------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()  # nvidia-smi needs ~1 s to start: sample from the warm-up on (same load), through the timed region
-    ctx.upload(win)
+    ctx.upload_batch(wins)
     t_warm = time.perf_counter()
     while True:  # at least W warm-up steps and ~1.5 s of load so that the clock samples cover the timed region
-        for _ in range(W):
-            flush_l2()
-            ctx.solve_resident()
+        timed_resident(ctx, W)
         if time.perf_counter() - t_warm > 1.5:
             break
     ctx.reset_stats()
     barrier()
     wall0 = time.perf_counter()
-    dev_ms, iters, edges = 0.0, 0, 0
-    for _ in range(K):
-        flush_l2()
-        r = ctx.solve_resident()
-        dev_ms += r.solve_ms
-        iters += len(r.trace)
-        edges += sum(t["n_active_edges"] for t in r.trace)
+    dev_ms, iters, edges = timed_resident(ctx, K)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     st = ctx.stats()
-    # ---- per-kernel-group device times: same K steps again with CUDA events around each group (this
+    # ---- per-kernel-group device times: the same steps again with CUDA events around each group (this
     #      pass launches the kernels one by one instead of through the CUDA graph; it is not the timed one)
     ctx.reset_stats()
     ctx.set_profiling(True)
-    for _ in range(K):
-        flush_l2()
-        ctx.solve_resident()
+    timed_resident(ctx, min(K, 5))
     stp = ctx.stats()
     ctx.set_profiling(False)
 
     # ---- end-to-end through the C ABI with host buffers --------------------------------------------
     for _ in range(2):
-        ctx.local_ba(win)
+        ctx.local_ba_batch(wins)
     barrier()
     e2e_s, e2e_iters = 0.0, 0
     for _ in range(K):
         flush_l2()
         t0 = time.perf_counter()
-        r2 = ctx.local_ba(win)
+        rs2 = ctx.local_ba_batch(wins)
         e2e_s += time.perf_counter() - t0
-        e2e_iters += len(r2.trace)
+        e2e_iters += sum(len(r.trace) for r in rs2)
     barrier()
-    h2d = (win.kf_state.nbytes + win.pt_xyz.nbytes + win.imu_preint.nbytes + 16 * win.n_obs + win.pt_obs_begin.nbytes
-           + 4 * win.n_kf + 8 * win.n_imu)
-    d2h = win.kf_state.nbytes + win.pt_xyz.nbytes + win.n_obs + 8 * win.n_obs
+    h2d = sum(window_bytes(w)[0] for w in wins)
+    d2h = sum(window_bytes(w)[1] for w in wins)
+
+    # ---- one window alone (BASELINE config 3: latency) ------------------------------------------------
+    single = None
+    if nw > 1 and not args.no_single:
+        c1 = api.Context(local_rank)
+        c1.upload_batch(wins[:1])
+        timed_resident(c1, W)
+        s_ms, s_iters, _ = timed_resident(c1, K)
+        for _ in range(2):
+            c1.local_ba(wins[0])
+        s_e2e, s_e2e_iters = 0.0, 0
+        for _ in range(K):
+            flush_l2()
+            t0 = time.perf_counter()
+            r1 = c1.local_ba(wins[0])
+            s_e2e += time.perf_counter() - t0
+            s_e2e_iters += len(r1.trace)
+        single = {"value": s_iters / (s_ms * 1e-3), "unit": UNIT, "ms_per_window": s_ms / K,
+                  "e2e": s_e2e_iters / s_e2e, "e2e_ms_per_window": 1e3 * s_e2e / K,
+                  "note": "ONE 20-KF window per call (BASELINE config 3): L2-resident and latency-bound"}
+        c1.close()
 
     # ---- reduce over ranks ----------------------------------------------------------------------------
     (dev_ms_max, e2e_s_max), (iters_all, e2e_iters_all, edges_all, launches_all) = sharding.reduce_bench(
@@ -244,66 +319,57 @@ def main():
 
     if rank == 0:
         peak, peak_src = _peaks()
-        n_red = 15 * win.n_free
-        b_lin = algorithmic_bytes_linearize(win)
+        n_red = 15 * wins[0].n_free
+        b_lin = sum(algorithmic_bytes_linearize(w) for w in wins)
         lin_us = 1e3 * stp.linearize_ms / max(1, stp.linearize_launches)
+        chol_us = 1e3 * stp.solve_ms / max(1, stp.solve_launches)
+        schur_us = 1e3 * stp.schur_ms / max(1, stp.schur_launches)
         achieved = b_lin / (lin_us * 1e-6) / 1e9 if lin_us > 0 else 0.0
+        ws_mb = nw * 21 if args.workload == "c3" else None
         line = {
             "metric": METRIC, "value": iters_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(win, args.workload), "l2": "flushed (256 MiB write) between steps",
-                       "windows_per_gpu": 1, "parallelism": f"independent windows x{world}",
-                       "timing": "CUDA events on the library stream around each solve, summed over steps, max over ranks"},
+            "config": {"workload": workload_desc(wins[0], args.workload, nw),
+                       "l2": "flushed (256 MiB write) between steps" + (f"; working set ~{ws_mb} MB per GPU" if ws_mb else ""),
+                       "windows_per_gpu": nw, "parallelism": f"independent windows, {nw} per GPU x {world} GPUs, no collective",
+                       "timing": "CUDA events on the library stream around each batched solve, summed over steps, max over ranks"},
             "edges_linearized_per_sec": edges_all / (dev_ms_max * 1e-3),
+            "windows_per_sec": nw * world * K / (dev_ms_max * 1e-3),
             "lm_iters_per_step": iters / K,
             "wall_s_timed_region": wall,
             "e2e": {"value": e2e_iters_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s_max / K},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s_max / K,
+                    "call": "vilba_local_ba_batch (host buffers in and out)" if nw > 1 else "vilba_local_ba"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"kernel": "linearize_v2_kernel + reduce_partials + assemble_hpp (linearize_imu_v2 beside it)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_LINEARIZE if args.workload == "c3" else None,
+            "roofline": {"kernel": "linearize_v2_kernel + reduce_partials + assemble_hpp (linearize_imu_v2 beside it)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("linearize_v2_kernel", nw, args.workload),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(b_lin),
                          "avg_launch_us": lin_us,
-                         "note": "linearize+accumulate (the kernel the north star names); one 20-KF window is a 7 MB, "
-                                 "L2-resident working set, so the kernel is latency-bound; traffic = dram read+write of "
-                                 "linearize_v2_kernel from profiles/r1_ncu_full_summary.txt"},
-            "roofline_dominant": {"kernel": "chol_cluster_kernel", "bound": "fp64 dependent-issue latency",
-                                  "share_of_step": (1e3 * stp.solve_ms / max(1, stp.solve_launches)) * (iters / K) / (1e3 * dev_ms_max / K) if dev_ms_max else None,
-                                  "achieved": (n_red ** 3 / 3.0 + 2.0 * n_red ** 2) / (1e-6 * max(1e-9, 1e3 * stp.solve_ms / max(1, stp.solve_launches))) / 1e12,
-                                  "peak": 37.2, "unit": "TFLOP/s", "peak_source": "148 SMs x 64 FP64 FMA/clk x 1.965 GHz (tools/ubench_fp64.cu measured 61.3/64)",
-                                  "note": "dense Cholesky of the 285x285 reduced camera system on one 8-CTA cluster: n sequential pivots"},
-            "kernels_us": {"linearize": lin_us,
-                           "schur": 1e3 * stp.schur_ms / max(1, stp.schur_launches),
-                           "chol_solve": 1e3 * stp.solve_ms / max(1, stp.solve_launches),
-                           "note": "CUDA events around each kernel group in a second, ungraphed pass over the same steps"},
+                         "note": "linearize+accumulate (the kernels the north star names) over all windows of the batch; "
+                                 "algorithmic bytes = SURVEY 8(d) B_lin summed over the windows; traffic = dram read+write "
+                                 "of linearize_v2_kernel per launch from the committed ncu --set full capture"},
+            "kernels_us": {"linearize": lin_us, "schur": schur_us, "chol_solve": chol_us,
+                           "note": "per batched launch; CUDA events around each kernel group in a second, ungraphed pass"},
+            "chol": {"kernel": "chol_cluster_kernel", "bound": "fp64 dependent-issue latency",
+                     "achieved_tflops": nw * (n_red ** 3 / 3.0 + 2.0 * n_red ** 2) / (1e-6 * max(1e-9, chol_us)) / 1e12,
+                     "peak_tflops": 37.2, "note": "dense Cholesky of the reduced camera systems, one 8-CTA cluster per window"},
         }
-        if world == 1 and not args.no_batch:
-            # independent windows through vilba_local_ba_batch (BASELINE config 5 shape on one GPU): host buffers in/out
-            nb = 32
-            base = [win] + [synth.make_config(args.workload, window_index=i) for i in range(1, 8)]
-            wins = [base[i % len(base)] for i in range(nb)]
-            ctx.local_ba_batch(wins[:8])
-            t0 = time.perf_counter()
-            rs = ctx.local_ba_batch(wins)
-            tb = time.perf_counter() - t0
-            line["batch"] = {"windows": nb, "lanes": 8, "value": sum(len(r.trace) for r in rs) / tb, "unit": UNIT,
-                             "windows_per_sec": nb / tb,
-                             "note": "vilba_local_ba_batch: independent windows solved concurrently (host buffers, end to end)"}
+        if single:
+            line["single_window"] = single
         if not args.no_cpu_baseline:
-            from oracle import pyoracle
-            pyoracle.local_ba(win)
-            c_iters, c_ms = 0, 0.0
+            threads = 1 if nw == 1 else min(host_threads(), nw)
             reps = 3
-            for _ in range(reps):
-                o = pyoracle.local_ba(win)
-                c_iters += len(o.trace)
-                c_ms += o.solve_ms
-            line["cpu_baseline"] = {"value": c_iters / (c_ms * 1e-3), "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{reps} full solves of the same window on 1 host core (oracle restatement; "
-                                              "faster than real g2o's MatrixXd path, so the ratio is conservative)"}
+            val, n_solved, _, _, _ = cpu_throughput(wins[:max(threads, 1)], threads, reps)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n_solved} window solves of the same workload on {threads} host threads, one "
+                                              "window per thread (oracle restatement; faster than real g2o's MatrixXd path, "
+                                              "so the ratio is conservative)"}
+            if threads > 1:
+                v1, _, _, _, _ = cpu_throughput(wins[:1], 1, 2)
+                line["cpu_baseline"]["single_thread_value"] = v1
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -103,7 +103,10 @@ struct DevWindow {
     double* lin_partial;     // lin_ctas * n_free * 27   per-CTA partial pose blocks of the mono edges
     double* imu_slot;        // NI * 930                 30x30 block + 30 rhs of every IMU edge pair
     double* mono_sum;        // n_free * 27              fixed-order sum of the CTA partials
-    double* Y;               // E * 24                   per trial: W D^-1 (18) and W (D^-1 b_l) (6)
+    double* Y;               // E * 24                   per trial: W D^-1 (18) and W (D^-1 b_l) (6)   (gather mode)
+    double* ts_rec;          // P * 12                   per trial, per point: D^-1, D^-1 b_l, observer masks (tile-scan mode)
+    unsigned* ts_hdr;        // tiles * 32               per trial, per tile: points observed by every key-frame
+    double* schur_partial;   // sp_grid * (n_pairs * 36 + n_free * 6)   partial sums of sum_l W D^-1 W^T (tile-scan mode)
     const int* blk_edge_i;   // n_free: IMU edge in which the block is key-frame i, or -1
     const int* blk_edge_j;   // n_free: IMU edge in which the block is key-frame j, or -1
     const int* edge_pt;      // E: map point of every mono edge           (built on the device, pairs.cu)
@@ -152,15 +155,25 @@ struct LaunchDims {
     int gather_grid;      // grid.x of the Schur gather (CTAs of 1024 threads looping over block pairs)
     int reduce_grid;      // grid.x of reduce_partials
     int assemble_grid;    // grid.x of assemble_hpp
+    int sp_warps;         // warps per CTA of the tile-scan Schur kernel; 0 => gather over pair lists instead
+    int sp_sets;          // the key-frame block pairs are cut into this many contiguous subsets (CTAs) ...
+    int sp_grid;          // ... and the points into this many subsets (= partial sums per window)
+    int sp_tile_pts;      // map points per shared-memory tile
     int chol_cluster;     // CTAs of the Cholesky cluster
     int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
     size_t smem_point;    // dynamic shared memory of update_eval / flags
     size_t smem_lin;      // ... of linearize_v2
     size_t smem_chol;     // ... of chol_cluster
+    size_t smem_sp;       // ... of schur_tile
 };
 size_t point_smem_bytes(int K);
 size_t linearize_smem_bytes(int K, int n_free);
 size_t chol_smem_bytes(int n);
+bool schur_tile_fits(int K, int n_free);   // the tile-scan Schur kernel handles windows of <= 32 key-frames
+size_t schur_tile_smem_bytes(int max_K, int tile_pts);
+size_t schur_tile_rec_doubles(int P);
+size_t schur_tile_hdr_words(int P, int tile_pts);
+size_t schur_partial_doubles(int n_free);
 bool chol_has_stage(int n_cap);
 int chol_block_size(int n_cap);
 cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels
@@ -179,6 +192,6 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
 cudaError_t launch_build_pair_lists(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_cull(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
-constexpr int kKernelsPerSlot = 10;
+constexpr int kKernelsPerSlot = 10;  // 11 in tile-scan Schur mode (records + tile + finish instead of prep + gather)
 
 }  // namespace vilba

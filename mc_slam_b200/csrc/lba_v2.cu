@@ -481,6 +481,253 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWi
 }
 
 // ------------------------------------------------------------------------------------------------
+// Schur complement, tile-scan formulation (windows with <= 32 key-frames: C1 / C3 / C5).
+//
+// Every thread OWNS one row of one key-frame block pair of S (pair (a <= b), row r: 6 accumulators in
+// registers), like the gather -- but instead of chasing precomputed (edge_a, edge_b) lists through L2 it
+// scans the window's map points tile by tile.  A tile (a few points, all their edges: one contiguous chunk
+// of W) is staged in shared memory together with Y = W D^-1 and W (D^-1 b_l); a 32-bit mask of the free
+// key-frames observing each point tells a thread in two instructions whether the point touches its pair,
+// and a popcount of the observer mask gives the local edge index.  W is read once per CTA, coalesced; no
+// atomics, fixed summation order => S is reproducible.  The pairs are cut into `sets` contiguous subsets
+// (consecutive pairs share key-frame a, so the lanes of a warp hit together) and the points into `gridDim.x /
+// sets` subsets whose partial sums the finish kernel adds in a fixed order.
+// (landmark loop of BlockSolver::solve, block_solver.hpp:381-439)
+// ------------------------------------------------------------------------------------------------
+// Per trial a small kernel writes one 96-byte record per map point (D^-1, D^-1 b_l, observer masks, first
+// edge inside its tile) and one 128-byte header per tile (for every key-frame the tile's points it observes),
+// so that a tile is three contiguous chunks of global memory: W of its edges, its records, its header.  The
+// tile kernel fetches them with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier) one tile ahead.
+constexpr int kTsRecDoubles = 12;  // D^-1 (6) | D^-1 b_l (3) | {observers, free observers} | {first edge, -} | pad
+constexpr int kTsHdrWords = 32;    // colmask[k]: bit l = point l of the tile has an active edge to key-frame k
+
+struct TsLayout {
+    size_t w, rec, hdr, buf_bytes, total;
+};
+__host__ __device__ static inline TsLayout ts_layout(int K, int tile_pts) {
+    TsLayout L;
+    const size_t edges = (size_t)tile_pts * (K < 32 ? K : 32);
+    L.w = 0;
+    L.rec = edges * 144;
+    L.hdr = L.rec + (size_t)tile_pts * 8 * kTsRecDoubles;
+    L.buf_bytes = L.hdr + 4 * kTsHdrWords;
+    L.total = 2 * L.buf_bytes + 64;
+    return L;
+}
+
+__host__ __device__ static inline size_t sp_acc_doubles(int nf) { return (size_t)(nf * (nf + 1) / 2) * 36 + (size_t)nf * 6; }
+size_t schur_partial_doubles(int n_free) { return sp_acc_doubles(n_free); }
+bool schur_tile_fits(int K, int n_free) { return K <= 32 && n_free <= 32; }
+size_t schur_tile_smem_bytes(int max_K, int tile_pts) { return ts_layout(max_K, tile_pts).total; }
+size_t schur_tile_rec_doubles(int P) { return (size_t)kTsRecDoubles * P; }
+size_t schur_tile_hdr_words(int P, int tile_pts) { return (size_t)kTsHdrWords * ((P + tile_pts - 1) / tile_pts) + 4; }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// one warp per tile, one lane per map point
+__global__ void __launch_bounds__(256) schur_rec_kernel(const DevWindow* __restrict__ wp, int tile_pts) {
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
+    if (w.lm->phase != PH_TRIAL) return;
+    const int lane = threadIdx.x & 31;
+    const int ntile = (w.P + tile_pts - 1) / tile_pts;
+    const double lambda = w.lm->lambda;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ntile; g += nw) {
+        const int p = g * tile_pts + lane;
+        const bool valid = lane < tile_pts && p < w.P;
+        unsigned am = 0, fm = 0;
+        if (valid) {
+            const int e0 = w.pt_obs_begin[p], e1 = w.pt_obs_begin[p + 1];
+            for (int e = e0; e < e1; ++e) {
+                const int rw = w.obs[e].w;
+                const int kf = rw & OBS_KF_MASK;
+                am |= 1u << kf;
+                if (!(rw & OBS_CULLED) && w.kf_block[kf] >= 0) fm |= 1u << kf;
+            }
+            const double* H = w.Hll + 6 * (size_t)p;
+            bool ok;
+            const S3 Dinv = s3_inverse(S3{H[0] + lambda, H[1], H[2], H[3] + lambda, H[4], H[5] + lambda}, ok);
+            const V3 db = s3_mul(Dinv, ld3(w.bl + 3 * (size_t)p));
+            double* d = w.ts_rec + (size_t)kTsRecDoubles * p;
+            d[0] = Dinv.xx, d[1] = Dinv.xy, d[2] = Dinv.xz, d[3] = Dinv.yy, d[4] = Dinv.yz, d[5] = Dinv.zz;
+            d[6] = db.x, d[7] = db.y, d[8] = db.z;
+            unsigned* u = reinterpret_cast<unsigned*>(d + 9);
+            u[0] = am, u[1] = fm, u[2] = (unsigned)(e0 - w.pt_obs_begin[g * tile_pts]), u[3] = 0u;
+        }
+        unsigned mine = 0;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const unsigned bal = __ballot_sync(0xffffffffu, valid && ((fm >> k) & 1u));
+            if (lane == k) mine = bal;
+        }
+        w.ts_hdr[(size_t)kTsHdrWords * g + lane] = mine;
+    }
+}
+
+__global__ void __launch_bounds__(512) schur_tile_kernel(const DevWindow* __restrict__ wp, int sets, int tile_pts) {
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
+    if (w.lm->phase != PH_TRIAL) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar[2];
+    const TsLayout L = ts_layout(w.K, tile_pts);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int set = blockIdx.x % sets, psub = blockIdx.x / sets, npsub = gridDim.x / sets;
+    // the row of S this thread owns
+    const int ppc = (w.n_pairs + sets - 1) / sets;  // pairs per set (contiguous)
+    const int slot = lane / 6, r = lane - 6 * slot;
+    const int pair_local = warp * 5 + slot;
+    const int pair = set * ppc + pair_local;
+    const bool live = lane < 30 && pair_local < ppc && pair < w.n_pairs;
+    int a = 0, b = 0, ka = 0, kb = 0;
+    if (live) {
+        a = w.pair_a[pair], b = w.pair_b[pair];
+        ka = w.blk_kf[a], kb = w.blk_kf[b];
+    }
+    const bool diag = live && a == b;
+    const unsigned below_a = (1u << ka) - 1u, below_b = (1u << kb) - 1u;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    double rb = 0.0;
+    const int ntile = (w.P + tile_pts - 1) / tile_pts;
+    const int g_begin = (int)((long long)ntile * psub / npsub), g_end = (int)((long long)ntile * (psub + 1) / npsub);
+    const int nt = g_end - g_begin;
+    const bool leader = threadIdx.x == 0;
+    if (leader) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // leader: bulk copies of tile g (edge range [e_lo, e_hi)) into buffer `b2`
+    auto issue = [&](int g, int b2, int e_lo, int e_hi) {
+        unsigned char* buf = smem_raw + (size_t)b2 * L.buf_bytes;
+        const int p0 = g * tile_pts, np = min(tile_pts, w.P - p0);
+        const unsigned wbytes = 144u * (unsigned)(e_hi - e_lo), rbytes = 8u * kTsRecDoubles * (unsigned)np, hbytes = 4u * kTsHdrWords;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic-proxy reads of the buffer
+        mbar_expect_tx(&bar[b2], wbytes + rbytes + hbytes);
+        if (wbytes) tma_load_1d(buf + L.w, w.W + 18 * (size_t)e_lo, wbytes, &bar[b2]);
+        tma_load_1d(buf + L.rec, w.ts_rec + (size_t)kTsRecDoubles * p0, rbytes, &bar[b2]);
+        tma_load_1d(buf + L.hdr, w.ts_hdr + (size_t)kTsHdrWords * g, hbytes, &bar[b2]);
+    };
+    auto tile_edges = [&](int t, int& e_lo, int& e_hi) {  // edge range of the t-th tile of this CTA
+        e_lo = e_hi = 0;
+        if (leader && t < nt) {
+            const int p0 = (g_begin + t) * tile_pts;
+            e_lo = w.pt_obs_begin[p0];
+            e_hi = w.pt_obs_begin[min(p0 + tile_pts, w.P)];
+        }
+    };
+    int e_lo_n, e_hi_n, e_lo_nn, e_hi_nn;
+    tile_edges(0, e_lo_n, e_hi_n);
+    if (leader && nt > 0) issue(g_begin, 0, e_lo_n, e_hi_n);
+    tile_edges(1, e_lo_n, e_hi_n);
+
+    for (int t = 0; t < nt; ++t) {
+        if (leader && t + 1 < nt) issue(g_begin + t + 1, (t + 1) & 1, e_lo_n, e_hi_n);  // its buffer was released by the barrier below
+        tile_edges(t + 2, e_lo_nn, e_hi_nn);  // in flight until the next iteration needs them
+        const unsigned char* buf = smem_raw + (size_t)(t & 1) * L.buf_bytes;
+        const double* bW = reinterpret_cast<const double*>(buf + L.w);
+        const double* bRec = reinterpret_cast<const double*>(buf + L.rec);
+        const unsigned* colmask = reinterpret_cast<const unsigned*>(buf + L.hdr);
+        mbar_wait(&bar[t & 1], (unsigned)((t >> 1) & 1));
+        // ---- the points of the tile that touch my block pair: two loads and an AND, then only the hits ----
+        unsigned hits = live ? (colmask[ka] & colmask[kb]) : 0u;
+        while (hits) {
+            const int l = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const double* d = bRec + kTsRecDoubles * l;
+            const uint2 mk = *reinterpret_cast<const uint2*>(d + 9);
+            const unsigned eb = *reinterpret_cast<const unsigned*>(d + 10);
+            const double* Wi = bW + 18 * (eb + __popc(mk.x & below_a)) + 3 * r;
+            const double2* Wj = reinterpret_cast<const double2*>(bW + 18 * (eb + __popc(mk.x & below_b)));
+            const double w0 = Wi[0], w1 = Wi[1], w2 = Wi[2];
+            // row r of W_i D^-1 (BDinv, block_solver.hpp:407)
+            const double y0 = fma(d[2], w2, fma(d[1], w1, d[0] * w0));
+            const double y1 = fma(d[4], w2, fma(d[3], w1, d[1] * w0));
+            const double y2 = fma(d[5], w2, fma(d[4], w1, d[2] * w0));
+            double wj[18];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double2 v = Wj[k];
+                wj[2 * k] = v.x, wj[2 * k + 1] = v.y;
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[c] = fma(y2, wj[3 * c + 2], fma(y1, wj[3 * c + 1], fma(y0, wj[3 * c], acc[c])));
+            if (diag) rb = fma(w2, d[8], fma(w1, d[7], fma(w0, d[6], rb)));  // rhs: b_s(a) -= W_a (D^-1 b_l)
+        }
+        e_lo_n = e_lo_nn, e_hi_n = e_hi_nn;
+        __syncthreads();  // tile t consumed: its buffer may be refilled
+    }
+    if (live) {
+        double* part = w.schur_partial + (size_t)psub * sp_acc_doubles(w.n_free);
+        double* d = part + (size_t)pair * 36 + 6 * r;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) d[c] = acc[c];
+        if (diag) part[(size_t)w.n_pairs * 36 + 6 * a + r] = rb;
+    }
+}
+
+// S = H_pp + lambda I - sum of the CTA partials (fixed order), b_s = b_p - sum; upper triangle only
+__global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __restrict__ wp, int point_ctas) {
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
+    if (w.lm->phase != PH_TRIAL) return;
+    const int n = w.n, nf = w.n_free;
+    const double lambda = w.lm->lambda;
+    const size_t accN = sp_acc_doubles(nf);
+    const size_t total = (size_t)n * n + n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const bool is_rhs = i >= (size_t)n * n;
+        int gr, gc;
+        if (is_rhs) {
+            gr = gc = (int)(i - (size_t)n * n);
+        } else {
+            gr = (int)(i / n);
+            gc = (int)(i - (size_t)gr * n);
+            if (gr > gc) continue;
+        }
+        const int a = gr / 15, b = gc / 15, rr = gr - 15 * a, cc = gc - 15 * b;
+        const int pr = pose6_index(rr), pc = pose6_index(cc);
+        double v = is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc];
+        if (!is_rhs && gr == gc) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
+        if (pr >= 0 && (is_rhs || pc >= 0)) {
+            const size_t off = is_rhs ? (size_t)(nf * (nf + 1) / 2) * 36 + 6 * a + pr
+                                      : (size_t)(a * nf - a * (a - 1) / 2 + (b - a)) * 36 + 6 * pr + pc;
+            double sum = 0.0;
+            for (int c = 0; c < point_ctas; ++c) sum += w.schur_partial[(size_t)c * accN + off];
+            v -= sum;
+        }
+        if (is_rhs)
+            w.bs[gr] = v;
+        else
+            w.S[(size_t)gr * w.lds + gc] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 size_t linearize_smem_bytes(int K, int n_free) { return linearize_v2_smem_bytes(K, n_free, kPointThreads / 32); }
@@ -495,6 +742,10 @@ cudaError_t configure_chol(const LaunchDims& d);
 cudaError_t configure_kernels(const LaunchDims& d) {
     cudaError_t e = cudaFuncSetAttribute(linearize_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_lin);
     if (e != cudaSuccess) return e;
+    if (d.smem_sp > 0) {
+        e = cudaFuncSetAttribute(schur_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_sp);
+        if (e != cudaSuccess) return e;
+    }
     e = configure_point_kernels(d);
     if (e != cudaSuccess) return e;
     return configure_chol(d);
@@ -518,9 +769,16 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     if ((e = launch_lm_iter_begin(s, wp, d)) != cudaSuccess) return e;
     // ---- one LM trial (skipped unless phase == TRIAL) ----
     if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
-    schur_prep_kernel<<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
-    if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;
-    schur_gather_kernel<<<dim3(d.gather_grid, d.n_windows), kSchurThreads, 0, s>>>(wp);
+    if (d.sp_warps > 0) {
+        schur_rec_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_tile_pts);
+        schur_tile_kernel<<<dim3(d.sp_grid * d.sp_sets, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_sets, d.sp_tile_pts);
+        if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;
+        schur_finish_kernel<<<dim3(d.assemble_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_grid);
+    } else {
+        schur_prep_kernel<<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
+        if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;
+        schur_gather_kernel<<<dim3(d.gather_grid, d.n_windows), kSchurThreads, 0, s>>>(wp);
+    }
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
     if ((e = launch_chol_cluster(s, wp, d)) != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;

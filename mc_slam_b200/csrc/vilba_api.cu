@@ -77,7 +77,7 @@ struct Layout {
     // work region; offsets relative to wk_base
     size_t edge_pt, pair_begin, pair_ea, pair_eb, pt_mask;
     size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y,
-        S, Lfac, cminv, cdinv, bs, x, dbg, outlier, wk_bytes;
+        schur_partial, ts_rec, ts_hdr, S, Lfac, cminv, cdinv, bs, x, dbg, outlier, wk_bytes;
 };
 
 struct WinMeta {
@@ -87,7 +87,8 @@ struct WinMeta {
     size_t in_base = 0, out_base = 0, wk_base = 0;
 };
 
-Layout make_layout(const WinMeta& m, int lin_ctas) {
+Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts) {
+    const bool gather = sp_ctas == 0;  // the pair lists and Y = W D^-1 only exist for the Schur gather
     const size_t K = m.K, NI = m.NI, P = m.P, E = m.E, n = m.n, n_free = m.n_free, n_pairs = m.n_pairs;
     Layout L;
     size_t o = 0;
@@ -119,8 +120,8 @@ Layout make_layout(const WinMeta& m, int lin_ctas) {
     o = 0;
     L.edge_pt = take(sizeof(int) * E);
     L.pair_begin = take(sizeof(int) * (n_pairs + 1));
-    L.pair_ea = take(sizeof(int) * m.n_triples);
-    L.pair_eb = take(sizeof(int) * m.n_triples);
+    L.pair_ea = take(gather ? sizeof(int) * m.n_triples : 0);
+    L.pair_eb = take(gather ? sizeof(int) * m.n_triples : 0);
     L.pt_mask = take(sizeof(unsigned long long) * 8 * P);
     for (int b = 0; b < 2; ++b) L.kf_state[b] = take(sizeof(double) * 22 * K);
     for (int b = 0; b < 2; ++b) L.pts[b] = take(sizeof(double) * 3 * P);
@@ -136,7 +137,10 @@ Layout make_layout(const WinMeta& m, int lin_ctas) {
     L.lin_partial = take(sizeof(double) * 27 * n_free * (size_t)lin_ctas);
     L.imu_slot = take(sizeof(double) * 930 * NI);
     L.mono_sum = take(sizeof(double) * 27 * n_free);
-    L.Y = take(sizeof(double) * 24 * E);
+    L.Y = take(gather ? sizeof(double) * 24 * E : 0);
+    L.schur_partial = take(sizeof(double) * schur_partial_doubles((int)n_free) * (size_t)sp_ctas);
+    L.ts_rec = take(gather ? 0 : sizeof(double) * schur_tile_rec_doubles((int)P) + 256);
+    L.ts_hdr = take(gather ? 0 : sizeof(unsigned) * schur_tile_hdr_words((int)P, tile_pts));
     const size_t lds = (n + 3) & ~(size_t)3;
     L.S = take(sizeof(double) * lds * n);
     L.Lfac = take(sizeof(double) * lds * n);
@@ -176,6 +180,9 @@ struct vilba_ctx {
     size_t in_total = 0, out_total = 0, lm_base = 0, out_region = 0;  // arena: [in | out | lm array | work]
     LaunchDims dims;
     int chol_cluster = 8;
+    bool schur_gather_only = false;  // env VILBA_SCHUR=gather (ablation)
+    int sp_grid_cap = 74;            // env VILBA_SP_GRID: point subsets per window of the tile-scan Schur kernel
+    int sp_sets = 0;                 // env VILBA_SP_SETS: block-pair subsets (0 = automatic)
     int cap_K = 0, cap_nf = 0, cap_n = 0;  // capacities the shared-memory sizes were configured for
     std::vector<GraphEntry> graphs;        // one captured LM slot per launch geometry
     bool use_graph = true;                 // env VILBA_GRAPH=0 launches the slot kernels one by one
@@ -256,11 +263,11 @@ void probe_drain(vilba_ctx* ctx) {
         cudaEventElapsedTime(&sch, p[2], p[3]);
         cudaEventElapsedTime(&chol, p[3], p[4]);
         // a slot whose group returned early (nothing to do in that phase) takes a few microseconds
-        if (lin > 0.008f * ctx->n_win) {
+        if (lin > 0.008f) {
             ctx->stats.linearize_ms += lin, ctx->stats.linearize_launches++;
             if (cudaEventElapsedTime(&t, p[0], p[7]) == cudaSuccess) ctx->dbg_ms[0] += t;  // mono linearize alone
         }
-        if (chol > 0.008f * ctx->n_win) {
+        if (chol > 0.012f) {
             ctx->stats.schur_ms += sch, ctx->stats.schur_launches++;
             ctx->stats.solve_ms += chol, ctx->stats.solve_launches++;
             if (cudaEventElapsedTime(&t, p[2], p[6]) == cudaSuccess) ctx->dbg_ms[1] += t;  // schur_prep alone
@@ -272,7 +279,7 @@ void probe_drain(vilba_ctx* ctx) {
 
 // launch geometry of a batch: the per-window grids shrink as the batch grows so that one launch is about
 // one resident wave (2 CTAs of the per-point kernels per SM) whatever the number of windows
-LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni) {
+LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, int max_nf) {
     LaunchDims d = ctx->dims;
     const int sm = ctx->sm_count;
     d.sm_count = sm;
@@ -282,7 +289,23 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni) {
     d.gather_grid = std::max(2, 2 * sm / n_win);
     d.reduce_grid = std::max(2, sm / n_win);
     d.assemble_grid = std::max(4, 8 * sm / n_win);
-    d.chol_cluster = ctx->chol_cluster;
+    // tile-scan Schur kernel for windows of <= 32 key-frames, else the gather over pair lists
+    d.sp_warps = d.sp_sets = d.sp_grid = d.sp_tile_pts = 0;
+    d.smem_sp = 0;
+    if (!ctx->schur_gather_only && max_K > 0 && schur_tile_fits(ctx->cap_K, ctx->cap_nf)) {
+        const int max_pairs = max_nf * (max_nf + 1) / 2;
+        d.sp_sets = ctx->sp_sets > 0 ? ctx->sp_sets : (max_pairs >= 40 ? 4 : 1);
+        d.sp_warps = std::min(16, std::max(1, ((max_pairs + d.sp_sets - 1) / d.sp_sets + 4) / 5));
+        d.sp_sets = (max_pairs + 5 * d.sp_warps - 1) / (5 * d.sp_warps);  // every pair must have a thread row
+        d.sp_grid = std::max(1, std::min(ctx->sp_grid_cap, 2 * sm / (d.sp_sets * n_win)));
+        d.sp_tile_pts = std::max(4, std::min(32, (int)(46 * 1024 / (144 * (size_t)std::min(32, max_K)))));
+        d.smem_sp = schur_tile_smem_bytes(max_K, d.sp_tile_pts);
+    }
+    // Cholesky: as many CTAs per window as the machine has to spare (one 8-CTA cluster for a single window,
+    // smaller clusters when many windows share the SMs: a CTA is more efficient the fewer partners it waits for)
+    int cl = 1;
+    while (2 * cl <= ctx->chol_cluster && 2 * cl * n_win <= sm) cl *= 2;
+    d.chol_cluster = n_win == 1 ? ctx->chol_cluster : cl;
     return d;
 }
 
@@ -376,6 +399,9 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.imu_slot = reinterpret_cast<double*>(wk + L.imu_slot);
     dw.mono_sum = reinterpret_cast<double*>(wk + L.mono_sum);
     dw.Y = reinterpret_cast<double*>(wk + L.Y);
+    dw.schur_partial = reinterpret_cast<double*>(wk + L.schur_partial);
+    dw.ts_rec = reinterpret_cast<double*>(wk + L.ts_rec);
+    dw.ts_hdr = reinterpret_cast<unsigned*>(wk + L.ts_hdr);
     dw.blk_edge_i = reinterpret_cast<const int*>(in + L.blk_edge_i);
     dw.blk_edge_j = reinterpret_cast<const int*>(in + L.blk_edge_j);
     dw.edge_pt = reinterpret_cast<const int*>(wk + L.edge_pt);
@@ -499,15 +525,16 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
             return VILBA_ERR_ARG;
         }
         ctx->dims.chol_cluster = ctx->chol_cluster;
+        ctx->dims.smem_sp = schur_tile_fits(ctx->cap_K, ctx->cap_nf) ? 110 * 1024 : 0;  // upper bound of any tile geometry
         CK(configure_kernels(ctx->dims), "cudaFuncSetAttribute");
         drop_graphs(ctx);
     }
-    ctx->dims = choose_dims(ctx, n_win, max_ni);
+    ctx->dims = choose_dims(ctx, n_win, max_ni, max_K, max_nf);
     // arena: [inputs of all windows | outputs of all windows | LmState array | work regions]
     size_t in_o = 0, out_o = 0, wk_o = 0;
     for (int i = 0; i < n_win; ++i) {
         WinMeta& m = meta[i];
-        m.L = make_layout(m, ctx->dims.point_grid);
+        m.L = make_layout(m, ctx->dims.point_grid, ctx->dims.sp_grid, std::max(1, ctx->dims.sp_tile_pts));
         m.in_base = in_o, in_o += m.L.in_bytes;
         m.out_base = out_o, out_o += m.L.out_bytes;
         m.wk_base = wk_o, wk_o += m.L.wk_bytes;
@@ -541,8 +568,11 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
                        ctx->stream), "H2D descriptors");
     // working copies of the estimates / observation table, then the Schur pair lists (they read the table)
     CK(launch_reset(ctx->stream, ctx->dwp, ctx->dims), "reset");
-    CK(launch_build_pair_lists(ctx->stream, ctx->dwp, ctx->dims), "pair lists");
-    ctx->stats.kernel_launches += 5;
+    if (ctx->dims.sp_warps == 0) {
+        CK(launch_build_pair_lists(ctx->stream, ctx->dwp, ctx->dims), "pair lists");
+        ctx->stats.kernel_launches += 4;
+    }
+    ctx->stats.kernel_launches += 1;
     ctx->n_win = n_win;
     return VILBA_OK;
 }
@@ -622,7 +652,7 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
                 CK(cudaGraphLaunch(exec, s), "graph launch");
             else
                 CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, probe_take(ctx)), "slot");
-            stt.kernel_launches += kKernelsPerSlot;
+            stt.kernel_launches += kKernelsPerSlot + (ctx->dims.sp_warps > 0 ? 1 : 0);
         }
         int r = read_lm(ctx, lm, stop_flag);
         if (r != VILBA_OK) return r;
@@ -795,9 +825,12 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     ctx->dims.chol_nb = 32;
     if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VILBA_SCHUR")) ctx->schur_gather_only = std::strcmp(e, "gather") == 0;
+    if (const char* e = std::getenv("VILBA_SP_GRID")) ctx->sp_grid_cap = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("VILBA_SP_SETS")) ctx->sp_sets = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_BATCH_LANES")) ctx->n_lanes = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_MAX_BATCH")) ctx->max_batch = std::max(1, std::min(kMaxBatch, std::atoi(e)));
-    ctx->dims = choose_dims(ctx, 1, 0);
+    ctx->dims = choose_dims(ctx, 1, 0, 0, 0);
     if (cudaMalloc(&ctx->dwp, sizeof(DevWindow) * kMaxBatch) != cudaSuccess) {
         delete ctx;
         return nullptr;
