@@ -30,8 +30,8 @@ __host__ __device__ static inline size_t kf_smem_bytes(int K) { return sizeof(do
 // NavState.cpp:81-109) the key-frame states.  CTA 0 publishes the updated states to the trial buffer.
 template <bool APPLY>
 __device__ __forceinline__ void kf_stage(const DevWindow& w, const KfSmem& s, int cur) {
-    const double* src = w.kf_state[cur];
-    double* dst = w.kf_state[cur ^ 1];
+    const double* src = (cur ? w.kf_state[1] : w.kf_state[0]);
+    double* dst = (cur ? w.kf_state[0] : w.kf_state[1]);
     const M3 Rcb = ldm3(w.Rcb);
     for (int k = threadIdx.x; k < w.K; k += blockDim.x) {
         const double* p = src + 22 * (size_t)k;

@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(kPointThreads) update_eval_kernel(const DevWin
     const int warps_per_cta = blockDim.x >> 5;
     const int gwarp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * warps_per_cta;
-    const double* pts_in = w.pts[cur];
-    double* pts_out = w.pts[cur ^ 1];
+    const double* pts_in = (cur ? w.pts[1] : w.pts[0]);
+    double* pts_out = (cur ? w.pts[0] : w.pts[1]);
     const int total = w.P + w.NI;
     double chi = 0.0, scale = 0.0;
 
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kPointThreads) flags_kernel(const DevWindow* _
     const int nwarps = gridDim.x * warps_per_cta;
     int cnt = 0;
     for (int p = gwarp; p < w.P; p += nwarps) {
-        const V3 Pw = ld3(w.pts[cur] + 3 * (size_t)p);
+        const V3 Pw = ld3((cur ? w.pts[1] : w.pts[0]) + 3 * (size_t)p);
         for (int e = w.pt_obs_begin[p] + lane; e < w.pt_obs_begin[p + 1]; e += 32) {
             int4 r = w.obs[e];
             const MonoObs o = load_obs(w.obs, e);
@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(256) export_kernel(const DevWindow* __restrict
     const DevWindow w = wp[blockIdx.y];
     const int cur = w.lm->cur;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-    for (int i = tid; i < 22 * w.K; i += nt) w.out_kf_state[i] = w.kf_state[cur][i];
-    for (int i = tid; i < 3 * w.P; i += nt) w.out_pts[i] = w.pts[cur][i];
+    for (int i = tid; i < 22 * w.K; i += nt) w.out_kf_state[i] = (cur ? w.kf_state[1] : w.kf_state[0])[i];
+    for (int i = tid; i < 3 * w.P; i += nt) w.out_pts[i] = (cur ? w.pts[1] : w.pts[0])[i];
     for (int i = tid; i < w.E; i += nt) {
         w.out_chi2[i] = w.obs_chi2[i];
         w.out_outlier[i] = w.outlier[i];

@@ -17,7 +17,15 @@
 
 namespace vilba {
 
-constexpr int kAccStride = 27;  // 21 upper entries of the 6x6 [P,Phi] block + 6 rhs entries
+constexpr int kAccStride = 27;
+
+// sum over the 8 lanes of a sub-warp group (xor tree: every lane gets the same bits)
+__device__ __forceinline__ double group8_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}  // 21 upper entries of the 6x6 [P,Phi] block + 6 rhs entries
 
 size_t linearize_v2_smem_bytes(int K, int n_free, int warps) {
     return kf_smem_bytes(K) + sizeof(double) * (size_t)warps * n_free * kAccStride + 16;
@@ -37,8 +45,8 @@ __global__ void __launch_bounds__(32) linearize_imu_v2_kernel(const DevWindow* _
     const int cur = w.lm->cur;
     for (int e = blockIdx.x; e < w.NI; e += gridDim.x) {
         const int ki = w.imu_i[e], kj = w.imu_j[e];
-        const double* si = w.kf_state[cur] + 22 * (size_t)ki;
-        const double* sj = w.kf_state[cur] + 22 * (size_t)kj;
+        const double* si = (cur ? w.kf_state[1] : w.kf_state[0]) + 22 * (size_t)ki;
+        const double* sj = (cur ? w.kf_state[1] : w.kf_state[0]) + 22 * (size_t)kj;
         const double* M = w.imu_preint + 142 * (size_t)e;
         for (int i = lane; i < 81; i += 32) Om[i] = w.imu_info[81 * (size_t)e + i];
         for (int i = lane; i < 216; i += 32) J[i] = 0.0;
@@ -172,20 +180,35 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
     __syncthreads();
     const int gwarp = blockIdx.x * warps_per_cta + warp;
     const int nwarps = point_ctas * warps_per_cta;
-    const double* pts = w.pts[cur];
+    const double* pts = (cur ? w.pts[1] : w.pts[0]);
     const M3 Rcb = ldm3(w.Rcb);
     double maxd = 0.0;
 
-    for (int p = gwarp; p < w.P; p += nwarps) {
-        const int e0i = w.pt_obs_begin[p], e1i = w.pt_obs_begin[p + 1];
-        const V3 Pw = ld3(pts + 3 * (size_t)p);
+    // 8 lanes per map point, 4 points per warp: a point has ~8 observations, so the lanes stay busy.  The pose-block
+    // sums go to the warp-private accumulator in four phases (one point at a time: the key-frames of ONE point
+    // are distinct, those of neighbouring points are not), which keeps the summation order fixed.
+    const int gl = lane & 7, grp = lane >> 3;
+    for (int base = gwarp * 4; base < w.P; base += nwarps * 4) {
+        const int p = base + grp;
+        const bool valid = p < w.P;
+        int e0i = 0, e1i = 0;
+        V3 Pw = v3(0, 0, 0);
+        if (valid) {
+            e0i = w.pt_obs_begin[p], e1i = w.pt_obs_begin[p + 1];
+            Pw = ld3(pts + 3 * (size_t)p);
+        }
+        const int rounds = __reduce_max_sync(0xffffffffu, (e1i - e0i + 7) >> 3);
         double hxx = 0, hxy = 0, hxz = 0, hyy = 0, hyz = 0, hzz = 0, bx = 0, by = 0, bz = 0;
-        for (int base = e0i; base < e1i; base += 32) {
-            const int e = base + lane;
-            if (e < e1i) {
+        for (int round = 0; round < rounds; ++round) {
+            const int e = e0i + 8 * round + gl;
+            const bool have = e < e1i;
+            bool to_pose = false;
+            int blk = -1;
+            double Jp[2][6], wgt = 0.0, wr0 = 0.0, wr1 = 0.0;
+            if (have) {
                 const MonoObs o = load_obs(w.obs, e);
                 double* Wp = w.W + 18 * (size_t)e;
-                const int blk = ks.blk[o.kf];
+                blk = ks.blk[o.kf];
                 bool wrote_w = false;
                 if (!o.culled) {
                     const double* cam = ks.cam + 12 * o.kf;
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                     V3 Paux, Pc;
                     mono_error(w, cam, Pw, o, r0, r1, Paux, Pc);
                     const double is2 = (double)o.is2;
-                    double wgt = is2;
+                    wgt = is2;
                     if (o.robust) {
                         double rho0, rho1;
                         huber(r0 * (is2 * r0) + r1 * (is2 * r1), w.huber_mono, rho0, rho1);
@@ -213,14 +236,15 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                     const double f10 = -(jc * HR.a10 + jd * HR.a20), f11 = -(jc * HR.a11 + jd * HR.a21),
                                  f12 = -(jc * HR.a12 + jd * HR.a22);
                     const double Jl[2][3] = {{l00, l01, l02}, {l10, l11, l12}};
-                    const double Jp[2][6] = {{-l00, -l01, -l02, f00, f01, f02}, {-l10, -l11, -l12, f10, f11, f12}};
+                    Jp[0][0] = -l00, Jp[0][1] = -l01, Jp[0][2] = -l02, Jp[0][3] = f00, Jp[0][4] = f01, Jp[0][5] = f02;
+                    Jp[1][0] = -l10, Jp[1][1] = -l11, Jp[1][2] = -l12, Jp[1][3] = f10, Jp[1][4] = f11, Jp[1][5] = f12;
                     hxx += wgt * (l00 * l00 + l10 * l10);
                     hxy += wgt * (l00 * l01 + l10 * l11);
                     hxz += wgt * (l00 * l02 + l10 * l12);
                     hyy += wgt * (l01 * l01 + l11 * l11);
                     hyz += wgt * (l01 * l02 + l11 * l12);
                     hzz += wgt * (l02 * l02 + l12 * l12);
-                    const double wr0 = -wgt * r0, wr1 = -wgt * r1;
+                    wr0 = -wgt * r0, wr1 = -wgt * r1;
                     bx += l00 * wr0 + l10 * wr1;
                     by += l01 * wr0 + l11 * wr1;
                     bz += l02 * wr0 + l12 * wr1;
@@ -231,19 +255,7 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                             for (int c = 0; c < 3; ++c)
                                 Wp[3 * r + c] = wgt * (Jp[0][r] * Jl[0][c] + Jp[1][r] * Jl[1][c]);
                         wrote_w = true;
-                        // warp-private accumulation: the lanes of this warp hold distinct key-frames
-                        double* a = acc + (size_t)blk * kAccStride;
-                        int idx = 0;
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                            for (int c = r; c < 6; ++c) {
-                                a[idx] += wgt * (Jp[0][r] * Jp[0][c] + Jp[1][r] * Jp[1][c]);
-                                ++idx;
-                            }
-                        }
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) a[21 + r] += Jp[0][r] * wr0 + Jp[1][r] * wr1;
+                        to_pose = true;
                     }
                 }
                 if (!wrote_w) {
@@ -251,12 +263,29 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                     for (int i = 0; i < 18; ++i) Wp[i] = 0.0;
                 }
             }
-            __syncwarp();  // a point with more than 32 observations revisits no key-frame, but keep smem ordered
+#pragma unroll 1
+            for (int ph = 0; ph < 4; ++ph) {
+                if (grp == ph && to_pose) {
+                    double* a = acc + (size_t)blk * kAccStride;
+                    int idx = 0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int c = r; c < 6; ++c) {
+                            a[idx] += wgt * (Jp[0][r] * Jp[0][c] + Jp[1][r] * Jp[1][c]);
+                            ++idx;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) a[21 + r] += Jp[0][r] * wr0 + Jp[1][r] * wr1;
+                }
+                __syncwarp();
+            }
         }
-        hxx = warp_sum(hxx), hxy = warp_sum(hxy), hxz = warp_sum(hxz);
-        hyy = warp_sum(hyy), hyz = warp_sum(hyz), hzz = warp_sum(hzz);
-        bx = warp_sum(bx), by = warp_sum(by), bz = warp_sum(bz);
-        if (lane == 0) {
+        hxx = group8_sum(hxx), hxy = group8_sum(hxy), hxz = group8_sum(hxz);
+        hyy = group8_sum(hyy), hyz = group8_sum(hyz), hzz = group8_sum(hzz);
+        bx = group8_sum(bx), by = group8_sum(by), bz = group8_sum(bz);
+        if (gl == 0 && valid) {
             double* H = w.Hll + 6 * (size_t)p;
             H[0] = hxx, H[1] = hxy, H[2] = hxz, H[3] = hyy, H[4] = hyz, H[5] = hzz;
             st3(w.bl + 3 * (size_t)p, v3(bx, by, bz));
