@@ -29,7 +29,7 @@ __device__ __forceinline__ double group8_sum(double v) {
 }
 
 template <bool APPLY>
-__global__ void __launch_bounds__(kPointThreads) update_eval_kernel(const DevWindow* __restrict__ wp) {
+__global__ void __launch_bounds__(kPointThreads, 2) update_eval_kernel(const DevWindow* __restrict__ wp) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (APPLY && w.lm->phase != PH_TRIAL) return;
     extern __shared__ double smem[];
@@ -37,6 +37,16 @@ __global__ void __launch_bounds__(kPointThreads) update_eval_kernel(const DevWin
     const int cur = w.lm->cur;
     const double lambda = w.lm->lambda;
     kf_stage<APPLY>(w, ks, cur);
+    // pose increments [dP, dPhi] of every key-frame (zeros for fixed ones) next to the states: the landmark
+    // back-substitution reads them per edge
+    double* xs6 = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + ((kf_smem_bytes(w.K) + 15) / 16) * 16);
+    if (APPLY) {
+        for (int i = threadIdx.x; i < 6 * w.K; i += blockDim.x) {
+            const int k = i / 6, c = i - 6 * k;
+            const int blk = w.kf_block[k];
+            xs6[i] = blk >= 0 ? w.x[15 * (size_t)blk + (c < 3 ? c : c + 3)] : 0.0;
+        }
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -64,11 +74,10 @@ __global__ void __launch_bounds__(kPointThreads) update_eval_kernel(const DevWin
             V3 acc = v3(0, 0, 0);
             for (int e = e0i + gl; e < e1i; e += 8) {
                 const int4 r = w.obs[e];
-                const int blk = ks.blk[r.w & OBS_KF_MASK];
-                if (!(r.w & OBS_CULLED) && blk >= 0) {
+                const int kf = r.w & OBS_KF_MASK;
+                if (!(r.w & OBS_CULLED) && ks.blk[kf] >= 0) {
                     const double* Wp = w.W + 18 * (size_t)e;
-                    const double* x = w.x + 15 * (size_t)blk;
-                    const double xs[6] = {x[0], x[1], x[2], x[6], x[7], x[8]};
+                    const double* xs = xs6 + 6 * kf;
 #pragma unroll
                     for (int rr = 0; rr < 6; ++rr) {
                         acc.x += Wp[3 * rr + 0] * xs[rr];
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(256) export_kernel(const DevWindow* __restrict
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-size_t point_smem_bytes(int K) { return kf_smem_bytes(K); }
+size_t point_smem_bytes(int K) { return kf_smem_bytes(K) + 16 + sizeof(double) * 6 * (size_t)K; }
 
 cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
     imu_prepare_kernel<<<dim3(d.imu_grid, d.n_windows), 32, 0, s>>>(wp);

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
             const bool have = e < e1i;
             bool to_pose = false;
             int blk = -1;
-            double Jp[2][6], wgt = 0.0, wr0 = 0.0, wr1 = 0.0;
+            double Jp[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, wgt = 0.0, wr0 = 0.0, wr1 = 0.0;
             if (have) {
                 const MonoObs o = load_obs(w.obs, e);
                 double* Wp = w.W + 18 * (size_t)e;
@@ -263,21 +263,36 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                     for (int i = 0; i < 18; ++i) Wp[i] = 0.0;
                 }
             }
+            // contributions of this edge to its key-frame's [P,Phi] block: 21 upper entries + 6 rhs entries
+            double ctr[kAccStride];
+            {
+                int idx = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int c = r; c < 6; ++c) {
+                        ctr[idx] = wgt * (Jp[0][r] * Jp[0][c] + Jp[1][r] * Jp[1][c]);
+                        ++idx;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) ctr[21 + r] = Jp[0][r] * wr0 + Jp[1][r] * wr1;
+            }
 #pragma unroll 1
             for (int ph = 0; ph < 4; ++ph) {
                 if (grp == ph && to_pose) {
                     double* a = acc + (size_t)blk * kAccStride;
-                    int idx = 0;
+                    // read - add - write in chunks of 9 so that the shared-memory round trips overlap
 #pragma unroll
-                    for (int r = 0; r < 6; ++r) {
+                    for (int ch = 0; ch < 3; ++ch) {
+                        double t[9];
 #pragma unroll
-                        for (int c = r; c < 6; ++c) {
-                            a[idx] += wgt * (Jp[0][r] * Jp[0][c] + Jp[1][r] * Jp[1][c]);
-                            ++idx;
-                        }
+                        for (int i = 0; i < 9; ++i) t[i] = a[9 * ch + i];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) t[i] += ctr[9 * ch + i];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) a[9 * ch + i] = t[i];
                     }
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) a[21 + r] += Jp[0][r] * wr0 + Jp[1][r] * wr1;
                 }
                 __syncwarp();
             }
@@ -617,6 +632,17 @@ __global__ void __launch_bounds__(256) schur_rec_kernel(const DevWindow* __restr
     }
 }
 
+// Work balance: a block pair (a, b) is touched by a point only if both key-frames observe it, which in a sliding
+// window is likely for close key-frames and rare for distant ones.  Every lane group therefore owns TWO pairs:
+// with the pairs ordered by distance d = b - a, group j takes the j-th closest and the j-th farthest, so the
+// hit counts of the groups (and of the warps) are nearly equal.
+__device__ __forceinline__ void ts_pair_by_distance(int q, int nf, int& a, int& b) {
+    int d = 0, off = 0;  // pairs with distance < d: d nf - d (d - 1) / 2
+    while (d < nf && off + (nf - d) <= q) off += nf - d, ++d;
+    a = q - off;
+    b = a + d;
+}
+
 __global__ void __launch_bounds__(512) schur_tile_kernel(const DevWindow* __restrict__ wp, int sets, int tile_pts) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_TRIAL) return;
@@ -625,21 +651,29 @@ __global__ void __launch_bounds__(512) schur_tile_kernel(const DevWindow* __rest
     const TsLayout L = ts_layout(w.K, tile_pts);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int set = blockIdx.x % sets, psub = blockIdx.x / sets, npsub = gridDim.x / sets;
-    // the row of S this thread owns
-    const int ppc = (w.n_pairs + sets - 1) / sets;  // pairs per set (contiguous)
+    // the two rows of S this thread owns
+    const int nf = w.n_free;
+    const int ngroups = (w.n_pairs + 1) / 2;
+    const int gpc = (ngroups + sets - 1) / sets;  // lane groups per set
     const int slot = lane / 6, r = lane - 6 * slot;
-    const int pair_local = warp * 5 + slot;
-    const int pair = set * ppc + pair_local;
-    const bool live = lane < 30 && pair_local < ppc && pair < w.n_pairs;
-    int a = 0, b = 0, ka = 0, kb = 0;
+    const int grp_local = warp * 5 + slot;
+    const int grp = set * gpc + grp_local;
+    const bool live = lane < 30 && grp_local < gpc && grp < ngroups;
+    int pa[2] = {0, 0}, pb[2] = {0, 0}, ka[2] = {0, 0}, kb[2] = {0, 0};
+    bool own[2] = {false, false};
     if (live) {
-        a = w.pair_a[pair], b = w.pair_b[pair];
-        ka = w.blk_kf[a], kb = w.blk_kf[b];
+        const int q2 = w.n_pairs - 1 - grp;
+        ts_pair_by_distance(grp, nf, pa[0], pb[0]);
+        own[0] = true;
+        if (q2 > grp) {
+            ts_pair_by_distance(q2, nf, pa[1], pb[1]);
+            own[1] = true;
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) ka[s2] = w.blk_kf[pa[s2]], kb[s2] = w.blk_kf[pb[s2]];
     }
-    const bool diag = live && a == b;
-    const unsigned below_a = (1u << ka) - 1u, below_b = (1u << kb) - 1u;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    double rb = 0.0;
+    double acc[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    double rb[2] = {0.0, 0.0};
     const int ntile = (w.P + tile_pts - 1) / tile_pts;
     const int g_begin = (int)((long long)ntile * psub / npsub), g_end = (int)((long long)ntile * (psub + 1) / npsub);
     const int nt = g_end - g_begin;
@@ -683,40 +717,49 @@ __global__ void __launch_bounds__(512) schur_tile_kernel(const DevWindow* __rest
         const double* bRec = reinterpret_cast<const double*>(buf + L.rec);
         const unsigned* colmask = reinterpret_cast<const unsigned*>(buf + L.hdr);
         mbar_wait(&bar[t & 1], (unsigned)((t >> 1) & 1));
-        // ---- the points of the tile that touch my block pair: two loads and an AND, then only the hits ----
-        unsigned hits = live ? (colmask[ka] & colmask[kb]) : 0u;
-        while (hits) {
-            const int l = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const double* d = bRec + kTsRecDoubles * l;
-            const uint2 mk = *reinterpret_cast<const uint2*>(d + 9);
-            const unsigned eb = *reinterpret_cast<const unsigned*>(d + 10);
-            const double* Wi = bW + 18 * (eb + __popc(mk.x & below_a)) + 3 * r;
-            const double2* Wj = reinterpret_cast<const double2*>(bW + 18 * (eb + __popc(mk.x & below_b)));
-            const double w0 = Wi[0], w1 = Wi[1], w2 = Wi[2];
-            // row r of W_i D^-1 (BDinv, block_solver.hpp:407)
-            const double y0 = fma(d[2], w2, fma(d[1], w1, d[0] * w0));
-            const double y1 = fma(d[4], w2, fma(d[3], w1, d[1] * w0));
-            const double y2 = fma(d[5], w2, fma(d[4], w1, d[2] * w0));
-            double wj[18];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const double2 v = Wj[k];
-                wj[2 * k] = v.x, wj[2 * k + 1] = v.y;
+        for (int s2 = 0; s2 < 2; ++s2) {
+            // the points of the tile that touch this block pair: two loads and an AND, then only the hits
+            unsigned hits = own[s2] ? (colmask[ka[s2]] & colmask[kb[s2]]) : 0u;
+            const unsigned below_a = (1u << ka[s2]) - 1u, below_b = (1u << kb[s2]) - 1u;
+            const bool diag = pa[s2] == pb[s2];
+            while (hits) {
+                const int l = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const double* d = bRec + kTsRecDoubles * l;
+                const uint2 mk = *reinterpret_cast<const uint2*>(d + 9);
+                const unsigned eb = *reinterpret_cast<const unsigned*>(d + 10);
+                const double* Wi = bW + 18 * (eb + __popc(mk.x & below_a)) + 3 * r;
+                const double2* Wj = reinterpret_cast<const double2*>(bW + 18 * (eb + __popc(mk.x & below_b)));
+                const double w0 = Wi[0], w1 = Wi[1], w2 = Wi[2];
+                // row r of W_i D^-1 (BDinv, block_solver.hpp:407)
+                const double y0 = fma(d[2], w2, fma(d[1], w1, d[0] * w0));
+                const double y1 = fma(d[4], w2, fma(d[3], w1, d[1] * w0));
+                const double y2 = fma(d[5], w2, fma(d[4], w1, d[2] * w0));
+                double wj[18];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const double2 v = Wj[k];
+                    wj[2 * k] = v.x, wj[2 * k + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    acc[s2][c] = fma(y2, wj[3 * c + 2], fma(y1, wj[3 * c + 1], fma(y0, wj[3 * c], acc[s2][c])));
+                if (diag) rb[s2] = fma(w2, d[8], fma(w1, d[7], fma(w0, d[6], rb[s2])));  // rhs: b_s(a) -= W_a (D^-1 b_l)
             }
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] = fma(y2, wj[3 * c + 2], fma(y1, wj[3 * c + 1], fma(y0, wj[3 * c], acc[c])));
-            if (diag) rb = fma(w2, d[8], fma(w1, d[7], fma(w0, d[6], rb)));  // rhs: b_s(a) -= W_a (D^-1 b_l)
         }
         e_lo_n = e_lo_nn, e_hi_n = e_hi_nn;
         __syncthreads();  // tile t consumed: its buffer may be refilled
     }
-    if (live) {
-        double* part = w.schur_partial + (size_t)psub * sp_acc_doubles(w.n_free);
-        double* d = part + (size_t)pair * 36 + 6 * r;
+    double* part = w.schur_partial + (size_t)psub * sp_acc_doubles(nf);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) d[c] = acc[c];
-        if (diag) part[(size_t)w.n_pairs * 36 + 6 * a + r] = rb;
+    for (int s2 = 0; s2 < 2; ++s2) {
+        if (!own[s2]) continue;
+        const int a = pa[s2], b = pb[s2];
+        double* d = part + (size_t)(a * nf - a * (a - 1) / 2 + (b - a)) * 36 + 6 * r;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) d[c] = acc[s2][c];
+        if (a == b) part[(size_t)w.n_pairs * 36 + 6 * a + r] = rb[s2];
     }
 }
 

@@ -295,8 +295,9 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
     if (!ctx->schur_gather_only && max_K > 0 && schur_tile_fits(ctx->cap_K, ctx->cap_nf)) {
         const int max_pairs = max_nf * (max_nf + 1) / 2;
         d.sp_sets = ctx->sp_sets > 0 ? ctx->sp_sets : (max_pairs >= 40 ? 4 : 1);
-        d.sp_warps = std::min(16, std::max(1, ((max_pairs + d.sp_sets - 1) / d.sp_sets + 4) / 5));
-        d.sp_sets = (max_pairs + 5 * d.sp_warps - 1) / (5 * d.sp_warps);  // every pair must have a thread row
+        const int max_groups = (max_pairs + 1) / 2;  // a lane group owns two block pairs (a close and a distant one)
+        d.sp_warps = std::min(16, std::max(1, ((max_groups + d.sp_sets - 1) / d.sp_sets + 4) / 5));
+        d.sp_sets = (max_groups + 5 * d.sp_warps - 1) / (5 * d.sp_warps);  // every group must have its lanes
         d.sp_grid = std::max(1, std::min(ctx->sp_grid_cap, 2 * sm / (d.sp_sets * n_win)));
         d.sp_tile_pts = std::max(4, std::min(32, (int)(46 * 1024 / (144 * (size_t)std::min(32, max_K)))));
         d.smem_sp = schur_tile_smem_bytes(max_K, d.sp_tile_pts);
