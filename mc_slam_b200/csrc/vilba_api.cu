@@ -300,6 +300,8 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
         d.sp_sets = (max_groups + 5 * d.sp_warps - 1) / (5 * d.sp_warps);  // every group must have its lanes
         d.sp_grid = std::max(1, std::min(ctx->sp_grid_cap, 2 * sm / (d.sp_sets * n_win)));
         d.sp_tile_pts = std::max(4, std::min(32, (int)(46 * 1024 / (144 * (size_t)std::min(32, max_K)))));
+        if (const char* e = std::getenv("VILBA_SP_PSUB")) d.sp_grid = std::max(1, std::atoi(e));
+        if (const char* e = std::getenv("VILBA_SP_TILE")) d.sp_tile_pts = std::max(2, std::min(d.sp_tile_pts, std::atoi(e)));
         d.smem_sp = schur_tile_smem_bytes(max_K, d.sp_tile_pts);
     }
     // Cholesky: as many CTAs per window as the machine has to spare (one 8-CTA cluster for a single window,
