@@ -199,6 +199,27 @@ int vilba_batch_solve_resident(vilba_ctx* ctx, int32_t n_windows, vilba_result* 
 int vilba_batch_download(vilba_ctx* ctx, int32_t n_windows, vilba_result* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * One LARGE window sharded by map point over the GPUs of a node (BASELINE config 4; one process per GPU).
+ * Every rank holds all key-frames and IMU edges and a contiguous range of the map points (with all their
+ * observations).  Per LM trial the ranks exchange, with ncclAllReduce over NVLink: H_pp | b_p (sum) and
+ * max |diag H_ll| (max) after the linearisation, the partial reduced camera systems S | b_s (sum) after the
+ * Schur step, and chi2 | gain-scale (sum) after the update; the reduced system is solved redundantly and the
+ * LM decisions are taken from the reduced (bit-identical) values, so the ranks never diverge.
+ *
+ *   rank 0:  vilba_comm_unique_id(id)  -> broadcast the 128 bytes to the other ranks (MPI, torch.distributed, ...)
+ *   all:     vilba_comm_init(ctx, id, rank, world)            (collective, once per context)
+ *   all:     vilba_shard_points(win, rank, world, &p0, &p1)   (which points this rank owns)
+ *   all:     vilba_local_ba(ctx, sub_window, out, NULL)       (collective; sub_window = all key-frames / IMU edges
+ *                                                              + the points [p0, p1) and their observations)
+ * Every rank returns the same key-frame states and ITS points / outlier flags; trace[i].n_active_edges counts the
+ * rank's own edges (the IMU edges on rank 0) and sums to the window's count over the ranks.  The stop flag is only
+ * honoured before the solve starts.  NCCL (libnccl.so.2) is loaded at run time by vilba_comm_init.
+ * ------------------------------------------------------------------------------------------- */
+int vilba_comm_unique_id(void* out128);
+int vilba_comm_init(vilba_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world);
+int vilba_shard_points(const vilba_window* win, int32_t rank, int32_t world, int32_t* p_begin, int32_t* p_end);
+
+/* ---------------------------------------------------------------------------------------------
  * Entry 2: batched IMU pre-integration.  Replaces the IMUPreintegrator::reset()+update() loop of
  * KeyFrame::ComputePreInt (src/KeyFrame.cpp:210-249) for n_pairs key-frame pairs at once.
  * Pair p integrates samples [sample_begin[p], sample_begin[p+1]); each sample is one update() call

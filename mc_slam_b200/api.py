@@ -114,6 +114,14 @@ class Context:
         self._check(self._lib.vilba_batch_download(self._h, n, crs), "vilba_batch_download")
         return results
 
+    # ---- one large window sharded by map point over the GPUs of a node ------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Collective: joins the NCCL communicator of the sharded solve (unique_id from comm_unique_id() on rank 0)."""
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.vilba_comm_init(self._h, buf, int(rank), int(world)), "vilba_comm_init")
+
     # ---- entry 2: IMUPreintegrator::update loop, batched ----------------------------------------
     def preintegrate_batch(self, sample_begin, gyro, acc, dt, bg, ba) -> np.ndarray:
         sb = np.ascontiguousarray(sample_begin, dtype=np.int32)
@@ -150,6 +158,14 @@ class Context:
 
     def set_profiling(self, on: bool):
         self._lib.vilba_set_profiling(self._h, int(bool(on)))
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (call on rank 0, broadcast the 128 bytes)."""
+    buf = C.create_string_buffer(128)
+    if capi.load_library().vilba_comm_unique_id(buf) != 0:
+        raise VilbaError("vilba_comm_unique_id failed (libnccl.so.2 not loadable)")
+    return buf.raw
 
 
 def max_batch() -> int:

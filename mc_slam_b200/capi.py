@@ -307,6 +307,9 @@ EXPORTED_SYMBOLS = [  # every symbol include/vilba.h declares
     "vilba_batch_upload",
     "vilba_batch_solve_resident",
     "vilba_batch_download",
+    "vilba_comm_unique_id",
+    "vilba_comm_init",
+    "vilba_shard_points",
     "vilba_preintegrate_batch",
     "vilba_preintegrate_batch_dev",
     "vilba_get_stats",
@@ -357,6 +360,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vilba_batch_solve_resident.restype = C.c_int
     lib.vilba_batch_download.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CResult)]
     lib.vilba_batch_download.restype = C.c_int
+    lib.vilba_comm_unique_id.argtypes = [C.c_void_p]
+    lib.vilba_comm_unique_id.restype = C.c_int
+    lib.vilba_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.vilba_comm_init.restype = C.c_int
+    lib.vilba_shard_points.argtypes = [C.POINTER(CWindow), C.c_int32, C.c_int32, _c_int32_p, _c_int32_p]
+    lib.vilba_shard_points.restype = C.c_int
     lib.vilba_preintegrate_batch.argtypes = [
         C.c_void_p, C.c_int32, _c_int32_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
         _c_double_p,

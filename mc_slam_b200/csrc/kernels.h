@@ -90,6 +90,13 @@ struct DevWindow {
     // normal equations
     double* Hpp;  // n * n   upper block triangle + full diagonal blocks
     double* bp;   // n
+    // where the assemble / Schur kernels WRITE: the same buffers for a whole window; this rank's partial sums
+    // (send buffers of the allreduce into Hpp|bp and S|bs) when the window is point-sharded over several GPUs
+    double* Hpp_w;
+    double* bp_w;
+    double* S_w;
+    double* bs_w;
+    int shard_owner;  // 1: this rank adds the terms that exist once per window (IMU edges, H_pp + lambda I in S); whole window: 1
     double* Hll;  // P * 6   (xx,xy,xz,yy,yz,zz)
     double* bl;   // P * 3
     double* W;    // E * 18  H_pl block of the edge, 6x3 rows [P,Phi]
@@ -144,6 +151,13 @@ cudaError_t launch_preint_batch(cudaStream_t stream, int n_pairs, const int* sam
                                 const double* acc, const double* dt, const double* bg, const double* ba,
                                 double* out, double gyr_cov, double acc_cov, int group);
 
+// point-sharded window: collectives the host controller inserts between the kernels of a slot
+enum SlotReduce { RED_HPP = 0, RED_MAXDIAG = 1, RED_S = 2, RED_CHI = 3 };
+struct SlotComm {
+    void* self;
+    cudaError_t (*reduce)(void* self, int which, cudaStream_t s);
+};
+
 // ---- local BA ------------------------------------------------------------------------------------
 // All kernels take a pointer to the device-resident DevWindow, so that their launch parameters do not
 // change between windows and one LM "slot" can be captured once in a CUDA graph.
@@ -188,7 +202,7 @@ cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, const Launch
 // `probe` (8 timing events, or NULL; [6] after schur_prep, [7] after linearize_v2): [0,1] linearize+reduce+assemble, [2,3] Schur prep+gather, [3,4] Cholesky,
 // [4,5] update+eval
 cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, const DevWindow* wp,
-                        const LaunchDims& d, cudaEvent_t* probe);
+                        const LaunchDims& d, cudaEvent_t* probe, const SlotComm* comm = nullptr);
 cudaError_t launch_build_pair_lists(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_cull(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kPointThreads, 2) update_eval_kernel(const Dev
     const int nwarps = gridDim.x * warps_per_cta;
     const double* pts_in = (cur ? w.pts[1] : w.pts[0]);
     double* pts_out = (cur ? w.pts[0] : w.pts[1]);
-    const int total = w.P + w.NI;
+    const int total = w.P + (w.shard_owner ? w.NI : 0);  // the IMU edges are evaluated by one rank of a sharded window
     double chi = 0.0, scale = 0.0;
 
     for (int base = gwarp * 4; base < total; base += nwarps * 4) {
@@ -215,7 +215,7 @@ __global__ void lm_stage_begin_kernel(const DevWindow* __restrict__ wp, int stag
         s->stage = stage;
         s->iter = 0;
         s->max_iters = max_iters;
-        s->n_active = w.E - s->n_culled + 2 * w.NI;
+        s->n_active = w.E - s->n_culled + (w.shard_owner ? 2 * w.NI : 0);  // sums to the window's count over the ranks
         // for (i < iterations && !terminate() && ok)   (sparse_optimizer.cpp:376)
         s->phase = (max_iters > 0 && !s->stop) ? PH_LINEARIZE : PH_DONE;
     }

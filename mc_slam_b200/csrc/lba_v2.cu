@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) assemble_hpp_kernel(const DevWindow* __re
             r = (int)(i / n);
             c = (int)(i - (size_t)r * n);
             if (r > c) {
-                w.Hpp[i] = 0.0;
+                w.Hpp_w[i] = 0.0;
                 continue;
             }
         }
@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(256) assemble_hpp_kernel(const DevWindow* __re
             v += w.mono_sum[(size_t)a * kAccStride + idx];
         }
         // IMU slots: the edge where block a is the "i" key-frame, then the one where it is the "j" key-frame
-        const int ea[2] = {w.blk_edge_i[a], w.blk_edge_j[a]};
+        // (added by one rank only when the window is sharded)
+        const int ea[2] = {w.shard_owner ? w.blk_edge_i[a] : -1, w.shard_owner ? w.blk_edge_j[a] : -1};
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int e = ea[s];
@@ -391,9 +392,9 @@ __global__ void __launch_bounds__(256) assemble_hpp_kernel(const DevWindow* __re
             v += is_rhs ? w.imu_slot[930 * (size_t)e + 900 + la] : w.imu_slot[930 * (size_t)e + 30 * la + lb];
         }
         if (is_rhs)
-            w.bp[r] = v;
+            w.bp_w[r] = v;
         else
-            w.Hpp[i] = v;
+            w.Hpp_w[i] = v;
     }
 }
 
@@ -507,18 +508,18 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWi
         const int rr = i / 15, c = i - 15 * rr;
         const int gr = 15 * a + rr, gc = 15 * b + c;
         if (gr > gc) continue;
-        double v = w.Hpp[(size_t)gr * n + gc];
-        if (gr == gc) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
+        double v = w.shard_owner ? w.Hpp[(size_t)gr * n + gc] : 0.0;
+        if (gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
         const int pr = pose6_index(rr), pc = pose6_index(c);
         if (pr >= 0 && pc >= 0) v -= blockacc[6 * pr + pc];
-        w.S[(size_t)gr * w.lds + gc] = v;
+        w.S_w[(size_t)gr * w.lds + gc] = v;
     }
     if (diag && threadIdx.x < 15) {
         const int rr = threadIdx.x;
-        double v = w.bp[15 * a + rr];
+        double v = w.shard_owner ? w.bp[15 * a + rr] : 0.0;
         const int pr = pose6_index(rr);
         if (pr >= 0) v -= blockacc[36 + pr];
-        w.bs[15 * a + rr] = v;
+        w.bs_w[15 * a + rr] = v;
     }
     __syncthreads();
     }
@@ -783,8 +784,8 @@ __global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __re
         }
         const int a = gr / 15, b = gc / 15, rr = gr - 15 * a, cc = gc - 15 * b;
         const int pr = pose6_index(rr), pc = pose6_index(cc);
-        double v = is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc];
-        if (!is_rhs && gr == gc) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
+        double v = !w.shard_owner ? 0.0 : (is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc]);
+        if (!is_rhs && gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
         if (pr >= 0 && (is_rhs || pc >= 0)) {
             const size_t off = is_rhs ? (size_t)(nf * (nf + 1) / 2) * 36 + 6 * a + pr
                                       : (size_t)(a * nf - a * (a - 1) / 2 + (b - a)) * 36 + 6 * pr + pc;
@@ -793,9 +794,9 @@ __global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __re
             v -= sum;
         }
         if (is_rhs)
-            w.bs[gr] = v;
+            w.bs_w[gr] = v;
         else
-            w.S[(size_t)gr * w.lds + gc] = v;
+            w.S_w[(size_t)gr * w.lds + gc] = v;
     }
 }
 
@@ -824,7 +825,7 @@ cudaError_t configure_kernels(const LaunchDims& d) {
 }
 
 cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, const DevWindow* wp,
-                        const LaunchDims& d, cudaEvent_t* probe) {
+                        const LaunchDims& d, cudaEvent_t* probe, const SlotComm* comm) {
     cudaError_t e;
     if (probe && (e = cudaEventRecord(probe[0], s)) != cudaSuccess) return e;
     // ---- linearise (skipped on the device unless phase == LINEARIZE): IMU edges beside the mono edges ----
@@ -837,6 +838,10 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     reduce_partials_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.point_grid);
     if ((e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) return e;
     assemble_hpp_kernel<<<dim3(d.assemble_grid, d.n_windows), 256, 0, s>>>(wp);
+    if (comm) {  // sharded window: H_pp | b_p = sum over ranks, max |diag H_ll| = max over ranks
+        if ((e = comm->reduce(comm->self, RED_HPP, s)) != cudaSuccess) return e;
+        if ((e = comm->reduce(comm->self, RED_MAXDIAG, s)) != cudaSuccess) return e;
+    }
     if (probe && (e = cudaEventRecord(probe[1], s)) != cudaSuccess) return e;
     if ((e = launch_lm_iter_begin(s, wp, d)) != cudaSuccess) return e;
     // ---- one LM trial (skipped unless phase == TRIAL) ----
@@ -851,10 +856,12 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
         if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;
         schur_gather_kernel<<<dim3(d.gather_grid, d.n_windows), kSchurThreads, 0, s>>>(wp);
     }
+    if (comm && (e = comm->reduce(comm->self, RED_S, s)) != cudaSuccess) return e;  // S | b_s = sum of the partial reduced systems
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
     if ((e = launch_chol_cluster(s, wp, d)) != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;
     if ((e = launch_update_eval_apply(s, wp, d)) != cudaSuccess) return e;
+    if (comm && (e = comm->reduce(comm->self, RED_CHI, s)) != cudaSuccess) return e;  // chi2 and the landmark part of the gain scale
     if (probe && (e = cudaEventRecord(probe[5], s)) != cudaSuccess) return e;
     if ((e = launch_lm_decide(s, wp, d)) != cudaSuccess) return e;
     return cudaGetLastError();

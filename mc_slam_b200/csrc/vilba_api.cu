@@ -9,6 +9,9 @@
 // A context holds a *batch* of 1..kMaxBatch independent windows.  Every kernel is launched once for the
 // whole batch (grid.y = window), each window carries its own device-resident LM controller, and a window
 // that has finished simply returns early from the remaining launches.  A single window is a batch of one.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -77,7 +80,7 @@ struct Layout {
     // work region; offsets relative to wk_base
     size_t edge_pt, pair_begin, pair_ea, pair_eb, pt_mask;
     size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y,
-        schur_partial, ts_rec, ts_hdr, S, Lfac, cminv, cdinv, bs, x, dbg, outlier, wk_bytes;
+        schur_partial, ts_rec, ts_hdr, S, Lfac, cminv, cdinv, bs, x, dbg, outlier, Hpp_part, S_part, hpp_span, s_span, wk_bytes;
 };
 
 struct WinMeta {
@@ -87,7 +90,7 @@ struct WinMeta {
     size_t in_base = 0, out_base = 0, wk_base = 0;
 };
 
-Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts) {
+Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bool sharded) {
     const bool gather = sp_ctas == 0;  // the pair lists and Y = W D^-1 only exist for the Schur gather
     const size_t K = m.K, NI = m.NI, P = m.P, E = m.E, n = m.n, n_free = m.n_free, n_pairs = m.n_pairs;
     Layout L;
@@ -130,7 +133,8 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts) {
     L.obs = take(sizeof(int4) * E);
     L.obs_chi2 = take(sizeof(double) * E);
     L.Hpp = take(sizeof(double) * n * n);
-    L.bp = take(sizeof(double) * n);
+    L.bp = take(sizeof(double) * n);  // directly behind H_pp (same reason)
+    L.hpp_span = L.bp + sizeof(double) * n - L.Hpp;
     L.Hll = take(sizeof(double) * 6 * P);
     L.bl = take(sizeof(double) * 3 * P);
     L.W = take(sizeof(double) * 18 * E);
@@ -143,13 +147,16 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts) {
     L.ts_hdr = take(gather ? 0 : sizeof(unsigned) * schur_tile_hdr_words((int)P, tile_pts));
     const size_t lds = (n + 3) & ~(size_t)3;
     L.S = take(sizeof(double) * lds * n);
+    L.bs = take(sizeof(double) * n);  // directly behind S: one allreduce covers S | b_s of a sharded window
+    L.s_span = L.bs + sizeof(double) * n - L.S;
     L.Lfac = take(sizeof(double) * lds * n);
     L.cminv = take(sizeof(double) * 256 * (n / 16 + 2));
     L.cdinv = take(sizeof(double) * n);
-    L.bs = take(sizeof(double) * n);
     L.x = take(sizeof(double) * n);
     L.dbg = take(sizeof(long long) * 16);
     L.outlier = take(E);
+    L.Hpp_part = take(sharded ? L.hpp_span : 0);  // send buffers of the two allreduces
+    L.S_part = take(sharded ? L.s_span : 0);
     L.wk_bytes = o;
     return L;
 }
@@ -189,6 +196,15 @@ struct vilba_ctx {
     // stats
     vilba_stats stats;
     bool profiling = false;
+    // point-sharded window over several GPUs (one process per GPU): NCCL is loaded at run time
+    void* nccl_lib = nullptr;
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    ncclResult_t (*p_ncclCommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*p_ncclCommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*p_ncclAllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*p_ncclGetErrorString)(ncclResult_t) = nullptr;
+    SlotComm slot_comm;
     std::vector<vilba_ctx*> lanes;  // sub-contexts of vilba_local_ba_batch: chunks of the batch are pipelined over them
     int n_lanes = 2;                // env VILBA_BATCH_LANES
     std::vector<cudaEvent_t> probes;  // 8 events per profiled slot
@@ -395,6 +411,10 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.obs_chi2 = reinterpret_cast<double*>(wk + L.obs_chi2);
     dw.Hpp = reinterpret_cast<double*>(wk + L.Hpp);
     dw.bp = reinterpret_cast<double*>(wk + L.bp);
+    const bool sharded = ctx->comm != nullptr;
+    dw.Hpp_w = sharded ? reinterpret_cast<double*>(wk + L.Hpp_part) : dw.Hpp;
+    dw.bp_w = sharded ? reinterpret_cast<double*>(wk + L.Hpp_part + (L.bp - L.Hpp)) : dw.bp;
+    dw.shard_owner = (!sharded || ctx->comm_rank == 0) ? 1 : 0;
     dw.Hll = reinterpret_cast<double*>(wk + L.Hll);
     dw.bl = reinterpret_cast<double*>(wk + L.bl);
     dw.W = reinterpret_cast<double*>(wk + L.W);
@@ -425,6 +445,8 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.cminv = reinterpret_cast<double*>(wk + L.cminv);
     dw.cdinv = reinterpret_cast<double*>(wk + L.cdinv);
     dw.bs = reinterpret_cast<double*>(wk + L.bs);
+    dw.S_w = sharded ? reinterpret_cast<double*>(wk + L.S_part) : dw.S;
+    dw.bs_w = sharded ? reinterpret_cast<double*>(wk + L.S_part + (L.bs - L.S)) : dw.bs;
     dw.x = reinterpret_cast<double*>(wk + L.x);
     dw.lm = lm;
     dw.dbg = reinterpret_cast<long long*>(wk + L.dbg);
@@ -462,6 +484,44 @@ void parallel_for(int n, int max_threads, F&& f) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// point-sharded window: the three exchanges of one LM slot, all on the library stream.
+// Every reduction goes from a send buffer that only this rank's kernels write into the buffer the next
+// kernel reads, so repeating it in a slot whose phase does not need it is harmless.
+// ------------------------------------------------------------------------------------------------
+void* open_nccl() {
+    static void* lib = nullptr;
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);  // the copy torch already loaded, if any
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return lib;
+}
+
+cudaError_t slot_reduce(void* self, int which, cudaStream_t s) {
+    vilba_ctx* ctx = static_cast<vilba_ctx*>(self);
+    const DevWindow& dw = ctx->dw[0];
+    const Layout& L = ctx->meta[0].L;
+    ncclResult_t r = ncclSuccess;
+    switch (which) {
+        case RED_HPP:
+            r = ctx->p_ncclAllReduce(dw.Hpp_w, dw.Hpp, L.hpp_span / sizeof(double), ncclDouble, ncclSum, ctx->comm, s);
+            break;
+        case RED_MAXDIAG:  // bits of non-negative doubles order like the values
+            r = ctx->p_ncclAllReduce(&dw.lm->maxdiag_bits, &dw.lm->maxdiag_bits, 1, ncclUint64, ncclMax, ctx->comm, s);
+            break;
+        case RED_S:
+            r = ctx->p_ncclAllReduce(dw.S_w, dw.S, L.s_span / sizeof(double), ncclDouble, ncclSum, ctx->comm, s);
+            break;
+        case RED_CHI:  // chi_acc and scale_acc are adjacent
+            r = ctx->p_ncclAllReduce(&dw.lm->chi_acc, &dw.lm->chi_acc, 2, ncclDouble, ncclSum, ctx->comm, s);
+            break;
+    }
+    if (r != ncclSuccess) {
+        ctx->err = std::string("ncclAllReduce: ") + (ctx->p_ncclGetErrorString ? ctx->p_ncclGetErrorString(r) : "?");
+        return cudaErrorUnknown;
+    }
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
 // flatten + upload a batch of windows
 // ------------------------------------------------------------------------------------------------
 int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
@@ -469,6 +529,10 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     ctx->n_win = 0;
     if (n_win <= 0 || n_win > ctx->max_batch || !wins) {
         ctx->err = "invalid batch size";
+        return VILBA_ERR_ARG;
+    }
+    if (ctx->comm && n_win != 1) {
+        ctx->err = "a sharded context solves one window at a time";
         return VILBA_ERR_ARG;
     }
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -537,7 +601,7 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     size_t in_o = 0, out_o = 0, wk_o = 0;
     for (int i = 0; i < n_win; ++i) {
         WinMeta& m = meta[i];
-        m.L = make_layout(m, ctx->dims.point_grid, ctx->dims.sp_grid, std::max(1, ctx->dims.sp_tile_pts));
+        m.L = make_layout(m, ctx->dims.point_grid, ctx->dims.sp_grid, std::max(1, ctx->dims.sp_tile_pts), ctx->comm != nullptr);
         m.in_base = in_o, in_o += m.L.in_bytes;
         m.out_base = out_o, out_o += m.L.out_bytes;
         m.wk_base = wk_o, wk_o += m.L.wk_bytes;
@@ -585,7 +649,7 @@ int read_lm(vilba_ctx* ctx, std::vector<LmState>& lm, const volatile uint8_t* st
     char* hp = ctx->pinned_out.base + ctx->out_total;
     const size_t bytes = sizeof(LmState) * (size_t)ctx->n_win;
     CK(cudaMemcpyAsync(hp, ctx->arena.base + ctx->lm_base, bytes, cudaMemcpyDeviceToHost, ctx->stream), "D2H lm");
-    if (stop_flag) {
+    if (stop_flag && !ctx->comm) {  // a sharded solve cannot be interrupted half way: the ranks would diverge
         bool sent = false;
         while (cudaStreamQuery(ctx->stream) == cudaErrorNotReady) {
             if (!sent && *stop_flag) {  // mirror of `bool* pbStopFlag` (sparse_optimizer.h:188)
@@ -637,9 +701,11 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
     // computeActiveErrors + activeRobustChi2 at the first iteration; later iterations inherit currentChi
     // of the accepted trial (identical by construction: the errors are those of the accepted state)
     CK(launch_eval_initial(s, ctx->dwp, ctx->dims), "eval");
+    const SlotComm* comm = ctx->comm ? &ctx->slot_comm : nullptr;
+    if (comm && slot_reduce(ctx, RED_CHI, s) != cudaSuccess) return VILBA_ERR_COMM;
     CK(launch_stage_begin(s, ctx->dwp, ctx->dims, stage, iterations), "stage_begin");
     stt.kernel_launches += 2;
-    const bool graph = ctx->use_graph && !ctx->profiling;
+    const bool graph = ctx->use_graph && !ctx->profiling && !comm;  // the collectives are enqueued between the kernels
     cudaGraphExec_t exec = nullptr;
     if (graph) {
         int r = ensure_graph(ctx, &exec);
@@ -654,7 +720,7 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
             if (graph)
                 CK(cudaGraphLaunch(exec, s), "graph launch");
             else
-                CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, probe_take(ctx)), "slot");
+                CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, probe_take(ctx), comm), "slot");
             stt.kernel_launches += kKernelsPerSlot + (ctx->dims.sp_warps > 0 ? 1 : 0);
         }
         int r = read_lm(ctx, lm, stop_flag);
@@ -859,6 +925,7 @@ void vilba_destroy(vilba_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (cudaEvent_t e : ctx->probes) cudaEventDestroy(e);
     drop_graphs(ctx);
+    if (ctx->comm && ctx->p_ncclCommDestroy) ctx->p_ncclCommDestroy(ctx->comm);
     if (ctx->dwp) cudaFree(ctx->dwp);
     ctx->arena.release();
     ctx->preint_arena.release();
@@ -912,6 +979,68 @@ int vilba_batch_solve_resident(vilba_ctx* ctx, int32_t n_windows, vilba_result* 
 int vilba_batch_download(vilba_ctx* ctx, int32_t n_windows, vilba_result* out) {
     if (!ctx || !out || n_windows != ctx->n_win) return VILBA_ERR_ARG;
     return download_batch(ctx, out);
+}
+
+// ---- one large window sharded by map point over the GPUs of a node (BASELINE config 4) ----
+int vilba_comm_unique_id(void* out128) {
+    if (!out128 || sizeof(ncclUniqueId) != 128) return VILBA_ERR_ARG;
+    void* lib = open_nccl();
+    if (!lib) return VILBA_ERR_COMM;
+    auto get = reinterpret_cast<ncclResult_t (*)(ncclUniqueId*)>(dlsym(lib, "ncclGetUniqueId"));
+    if (!get || get(static_cast<ncclUniqueId*>(out128)) != ncclSuccess) return VILBA_ERR_COMM;
+    return VILBA_OK;
+}
+
+int vilba_comm_init(vilba_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world) {
+    if (!ctx || !unique_id128 || world < 1 || rank < 0 || rank >= world || ctx->comm) return VILBA_ERR_ARG;
+    void* lib = open_nccl();
+    if (!lib) {
+        ctx->err = "libnccl.so.2 not found";
+        return VILBA_ERR_COMM;
+    }
+    ctx->nccl_lib = lib;
+    ctx->p_ncclCommInitRank = reinterpret_cast<decltype(ctx->p_ncclCommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    ctx->p_ncclCommDestroy = reinterpret_cast<decltype(ctx->p_ncclCommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    ctx->p_ncclAllReduce = reinterpret_cast<decltype(ctx->p_ncclAllReduce)>(dlsym(lib, "ncclAllReduce"));
+    ctx->p_ncclGetErrorString = reinterpret_cast<decltype(ctx->p_ncclGetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!ctx->p_ncclCommInitRank || !ctx->p_ncclAllReduce || !ctx->p_ncclCommDestroy) {
+        ctx->err = "NCCL symbols missing";
+        return VILBA_ERR_COMM;
+    }
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id128, sizeof(id));
+    const ncclResult_t r = ctx->p_ncclCommInitRank(&ctx->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        ctx->comm = nullptr;
+        ctx->err = std::string("ncclCommInitRank: ") + (ctx->p_ncclGetErrorString ? ctx->p_ncclGetErrorString(r) : "?");
+        return VILBA_ERR_COMM;
+    }
+    ctx->comm_rank = rank, ctx->comm_world = world;
+    ctx->slot_comm.self = ctx;
+    ctx->slot_comm.reduce = slot_reduce;
+    ctx->n_win = 0;  // layouts depend on the mode
+    return VILBA_OK;
+}
+
+int vilba_shard_points(const vilba_window* win, int32_t rank, int32_t world, int32_t* p_begin, int32_t* p_end) {
+    if (!win || world < 1 || rank < 0 || rank >= world || !p_begin || !p_end) return VILBA_ERR_ARG;
+    // contiguous point ranges balanced by edge count: rank r owns the points whose first edge lies in
+    // [E r / world, E (r + 1) / world)
+    auto cut = [&](int r) {
+        if (r <= 0) return 0;
+        if (r >= world) return (int)win->n_pts;
+        const long long target = (long long)win->n_obs * r / world;
+        int lo = 0, hi = win->n_pts;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (win->pt_obs_begin[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    *p_begin = win->n_pts ? cut(rank) : 0;
+    *p_end = win->n_pts ? cut(rank + 1) : 0;
+    return VILBA_OK;
 }
 
 int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, const volatile uint8_t* stop_flag) {
