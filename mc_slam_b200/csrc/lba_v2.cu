@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                         wgt = rho1 * is2;
                     }
                     const M3 Rcw = ldm3(cam);
-                    const double z = Pc.z;
-                    const double ja = w.fx / z, jb = (-Pc.x / z * w.fx) / z;
-                    const double jc = w.fy / z, jd = (-Pc.y / z * w.fy) / z;
+                    const double iz = 1.0 / Pc.z;  // see mono_error: one reciprocal for the six divisions by z
+                    const double ja = w.fx * iz, jb = (-(Pc.x * iz) * w.fx) * iz;
+                    const double jc = w.fy * iz, jd = (-(Pc.y * iz) * w.fy) * iz;
                     const double l00 = -(ja * Rcw.a00 + jb * Rcw.a20), l01 = -(ja * Rcw.a01 + jb * Rcw.a21),
                                  l02 = -(ja * Rcw.a02 + jb * Rcw.a22);
                     const double l10 = -(jc * Rcw.a10 + jd * Rcw.a20), l11 = -(jc * Rcw.a11 + jd * Rcw.a21),
