@@ -92,6 +92,11 @@ class Context:
         self._check(self._lib.vilba_window_download(self._h, C.byref(cr)), "vilba_window_download")
         return res
 
+    # ---- the same two calls with caller-owned, reusable buffers (what a C++ caller does) -----------
+    def prepare(self, wins: Sequence[Window]) -> "PreparedBatch":
+        """Allocates the result arrays and the ctypes views of `wins` once; run() is then only the C-ABI call."""
+        return PreparedBatch(self, list(wins))
+
     # ---- resident batch of independent windows (one batched launch per kernel) --------------------
     def upload_batch(self, wins: Sequence[Window]):
         self._keep_batch = list(wins)
@@ -158,6 +163,33 @@ class Context:
 
     def set_profiling(self, on: bool):
         self._lib.vilba_set_profiling(self._h, int(bool(on)))
+
+
+class PreparedBatch:
+    """Host buffers of a batch, owned by the caller and reused across calls: the inputs as ctypes views of the
+    numpy arrays, the outputs pre-allocated.  run() = vilba_local_ba_batch (or vilba_local_ba for one window)."""
+
+    def __init__(self, ctx: Context, wins: List[Window]):
+        self.ctx, self.wins = ctx, wins
+        n = len(wins)
+        self.results = [Result.alloc(w) for w in wins]
+        for r in self.results:  # touch the pages now: the first write is otherwise paid inside the call
+            r.kf_state.fill(0), r.pt_xyz.fill(0), r.obs_outlier.fill(0), r.obs_chi2.fill(0)
+        self._cws = (CWindow * n)(*[w.as_c() for w in wins])
+        self._crs = (CResult * n)(*[r.as_c() for r in self.results])
+
+    def run(self) -> List[Result]:
+        lib, h, n = self.ctx._lib, self.ctx._h, len(self.wins)
+        if n == 1:
+            st = lib.vilba_local_ba(h, C.byref(self._cws[0]), C.byref(self._crs[0]), None)
+        else:
+            st = lib.vilba_local_ba_batch(h, n, self._cws, self._crs)
+        self.ctx._check(st, "vilba_local_ba(_batch)")
+        return self.results
+
+    def collect(self) -> List[Result]:
+        """Copies status / trace out of the C structs (not part of the timed call)."""
+        return [r.take(self._crs[i]) for i, r in enumerate(self.results)]
 
 
 def comm_unique_id() -> bytes:

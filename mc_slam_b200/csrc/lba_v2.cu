@@ -731,18 +731,16 @@ __global__ void __launch_bounds__(512) schur_tile_kernel(const DevWindow* __rest
                 const uint2 mk = *reinterpret_cast<const uint2*>(d + 9);
                 const unsigned eb = *reinterpret_cast<const unsigned*>(d + 10);
                 const double* Wi = bW + 18 * (eb + __popc(mk.x & below_a)) + 3 * r;
-                const double2* Wj = reinterpret_cast<const double2*>(bW + 18 * (eb + __popc(mk.x & below_b)));
+                const double* Wj = bW + 18 * (eb + __popc(mk.x & below_b));
                 const double w0 = Wi[0], w1 = Wi[1], w2 = Wi[2];
                 // row r of W_i D^-1 (BDinv, block_solver.hpp:407)
                 const double y0 = fma(d[2], w2, fma(d[1], w1, d[0] * w0));
                 const double y1 = fma(d[4], w2, fma(d[3], w1, d[1] * w0));
                 const double y2 = fma(d[5], w2, fma(d[4], w1, d[2] * w0));
+                // the 6 row lanes of a pair read the same W_j (a broadcast)
                 double wj[18];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const double2 v = Wj[k];
-                    wj[2 * k] = v.x, wj[2 * k + 1] = v.y;
-                }
+                for (int k = 0; k < 18; ++k) wj[k] = Wj[k];
 #pragma unroll
                 for (int c = 0; c < 6; ++c)
                     acc[s2][c] = fma(y2, wj[3 * c + 2], fma(y1, wj[3 * c + 1], fma(y0, wj[3 * c], acc[s2][c])));
