@@ -181,7 +181,7 @@ int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out,
                    const volatile uint8_t* stop_flag);
 
 /* Many independent windows in one call (BASELINE config 5).  The windows are solved in batched launches
- * (chunks of vilba_max_batch() windows, pipelined); out[i] corresponds to win[i]. */
+ * (a few concurrent lanes of up to vilba_max_batch() windows each); out[i] corresponds to win[i]. */
 int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win, vilba_result* out);
 
 /* Device-resident variant used to time the solve without host<->device copies:
@@ -190,10 +190,14 @@ int vilba_window_upload(vilba_ctx* ctx, const vilba_window* win);
 int vilba_window_solve_resident(vilba_ctx* ctx, vilba_result* out /* only status/trace/solve_ms filled */);
 int vilba_window_download(vilba_ctx* ctx, vilba_result* out);
 
-/* The same for a resident batch of 1..vilba_max_batch() independent windows: every kernel is launched once
- * for the whole batch (one grid row per window) and each window runs its own device-side LM controller.
- * out[i].solve_ms is the device time of the whole batch. */
+/* The same for a resident batch of independent windows: every kernel is launched once per lane for all the
+ * lane's windows (one grid row per window) and each window runs its own device-side LM controller; batches of
+ * 16 or more windows are split over up to 3 lanes (env VILBA_BATCH_LANES) that run concurrently.
+ * out[i].solve_ms is the device time of the whole batch (first kernel of any lane to the last). */
 int vilba_max_batch(void);
+/* lanes (concurrent sub-batches, each with its own streams) the resident batch is split over: a launch of any
+ * kernel covers n_windows / vilba_batch_groups() windows */
+int vilba_batch_groups(const vilba_ctx* ctx);
 int vilba_batch_upload(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win);
 int vilba_batch_solve_resident(vilba_ctx* ctx, int32_t n_windows, vilba_result* out);
 int vilba_batch_download(vilba_ctx* ctx, int32_t n_windows, vilba_result* out);

@@ -104,6 +104,9 @@ class Context:
         cws = (CWindow * n)(*[w.as_c() for w in wins])
         self._check(self._lib.vilba_batch_upload(self._h, n, cws), "vilba_batch_upload")
 
+    def batch_groups(self) -> int:
+        return int(self._lib.vilba_batch_groups(self._h))
+
     def solve_batch_resident(self) -> List[Result]:
         n = len(self._keep_batch)
         crs = (CResult * n)()

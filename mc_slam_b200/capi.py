@@ -305,6 +305,7 @@ EXPORTED_SYMBOLS = [  # every symbol include/vilba.h declares
     "vilba_window_download",
     "vilba_max_batch",
     "vilba_batch_upload",
+    "vilba_batch_groups",
     "vilba_batch_solve_resident",
     "vilba_batch_download",
     "vilba_comm_unique_id",
@@ -354,6 +355,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vilba_window_download.restype = C.c_int
     lib.vilba_max_batch.argtypes = []
     lib.vilba_max_batch.restype = C.c_int
+    lib.vilba_batch_groups.argtypes = [C.c_void_p]
+    lib.vilba_batch_groups.restype = C.c_int
     lib.vilba_batch_upload.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CWindow)]
     lib.vilba_batch_upload.restype = C.c_int
     lib.vilba_batch_solve_resident.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CResult)]

@@ -205,8 +205,14 @@ struct vilba_ctx {
     ncclResult_t (*p_ncclAllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*p_ncclGetErrorString)(ncclResult_t) = nullptr;
     SlotComm slot_comm;
+    // a large batch is split over a few sub-contexts ("lanes": own streams, arena, graphs, one host thread each)
+    // whose batched solves run concurrently: the kernels are latency-bound, a second and third stream fill the SMs
+    int split = 0;                       // lanes the resident batch is split over (0: it lives in this context)
+    std::vector<int> split_first;        // first window of every lane (+ end)
+    cudaEvent_t start_after = nullptr;   // lane: event of the parent stream the solve starts after
+    cudaEvent_t ev_done = nullptr;       // lane: recorded behind the last kernel of a solve
     std::vector<vilba_ctx*> lanes;  // sub-contexts of vilba_local_ba_batch: chunks of the batch are pipelined over them
-    int n_lanes = 2;                // env VILBA_BATCH_LANES
+    int n_lanes = 3;                // env VILBA_BATCH_LANES
     std::vector<cudaEvent_t> probes;  // 8 events per profiled slot
     size_t probes_used = 0;
     double dbg_ms[4] = {0, 0, 0, 0};
@@ -782,6 +788,7 @@ int solve_batch(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     cudaStream_t s = ctx->stream;
     debug_counters(ctx);
+    if (ctx->start_after) CK(cudaStreamWaitEvent(s, ctx->start_after, 0), "wait start");
     CK(launch_reset(s, ctx->dwp, ctx->dims), "reset");  // every solve restarts from the uploaded state
     CK(cudaEventRecord(ctx->ev_a, s), "event");
     CK(launch_imu_prepare(s, ctx->dwp, ctx->dims), "imu_prepare");
@@ -805,6 +812,7 @@ int solve_batch(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_
     CK(launch_final_flags(s, ctx->dwp, ctx->dims), "final_flags");
     ctx->stats.kernel_launches += 1;
     CK(cudaEventRecord(ctx->ev_b, s), "event");
+    if (ctx->ev_done) CK(cudaEventRecord(ctx->ev_done, s), "event");
     CK(cudaStreamSynchronize(s), "sync");
     probe_drain(ctx);
     float ms = 0.f;
@@ -842,6 +850,100 @@ void add_stats(vilba_stats& a, const vilba_stats& b) {
     a.linearize_ms += b.linearize_ms, a.linearize_launches += b.linearize_launches;
     a.schur_ms += b.schur_ms, a.schur_launches += b.schur_launches;
     a.solve_ms += b.solve_ms, a.solve_launches += b.solve_launches;
+}
+
+// ---- a batch split over lanes ---------------------------------------------------------------------
+int ensure_lanes(vilba_ctx* ctx, int lanes) {
+    while ((int)ctx->lanes.size() < lanes) {
+        vilba_ctx* sub = vilba_create(ctx->device, &ctx->prm);
+        if (!sub) {
+            ctx->err = "could not create a batch lane";
+            return VILBA_ERR_CUDA;
+        }
+        sub->max_batch = ctx->max_batch;
+        if (cudaEventCreateWithFlags(&sub->ev_done, cudaEventDisableTiming) != cudaSuccess) return VILBA_ERR_CUDA;
+        ctx->lanes.push_back(sub);
+    }
+    return VILBA_OK;
+}
+
+// how many lanes a batch of n windows is split over, and where the cuts are
+int plan_split(const vilba_ctx* ctx, int n, std::vector<int>& first) {
+    int lanes = 1;
+    if (!ctx->comm && ctx->n_lanes > 1 && n >= 16) lanes = std::min(ctx->n_lanes, n / 8);
+    lanes = std::max(lanes, (n + ctx->max_batch - 1) / ctx->max_batch);
+    first.assign(lanes + 1, 0);
+    for (int l = 0; l <= lanes; ++l) first[l] = (int)((long long)n * l / lanes);
+    return lanes;
+}
+
+template <class F>
+int for_each_lane(vilba_ctx* ctx, int lanes, bool concurrent, F&& f) {
+    std::vector<int> status(lanes, VILBA_OK);
+    if (concurrent && lanes > 1) {
+        std::vector<std::thread> th;
+        for (int l = 0; l < lanes; ++l) th.emplace_back([&, l]() { status[l] = f(l); });
+        for (auto& t : th) t.join();
+    } else {
+        for (int l = 0; l < lanes; ++l) status[l] = f(l);
+    }
+    int worst = VILBA_OK;
+    for (int l = 0; l < lanes; ++l) {
+        add_stats(ctx->stats, ctx->lanes[l]->stats);
+        std::memset(&ctx->lanes[l]->stats, 0, sizeof(vilba_stats));
+        if (status[l] != VILBA_OK && worst >= 0) {
+            worst = status[l];
+            ctx->err = ctx->lanes[l]->err;
+        }
+    }
+    return worst;
+}
+
+int upload_split(vilba_ctx* ctx, int n, const vilba_window* wins) {
+    ctx->split = 0;
+    ctx->n_win = 0;
+    if (n <= 0 || !wins) return VILBA_ERR_ARG;
+    const int lanes = plan_split(ctx, n, ctx->split_first);
+    if (lanes == 1) return upload_batch(ctx, n, wins);
+    int r = ensure_lanes(ctx, lanes);
+    if (r != VILBA_OK) return r;
+    r = for_each_lane(ctx, lanes, true, [&](int l) {
+        return upload_batch(ctx->lanes[l], ctx->split_first[l + 1] - ctx->split_first[l], wins + ctx->split_first[l]);
+    });
+    if (r == VILBA_OK) ctx->split = lanes;
+    return r;
+}
+
+int solve_split(vilba_ctx* ctx, vilba_result* out) {
+    if (!ctx->split) return solve_batch(ctx, out, nullptr);
+    const int lanes = ctx->split;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaEventRecord(ctx->ev_a, ctx->stream), "event");
+    for (int l = 0; l < lanes; ++l) {
+        ctx->lanes[l]->start_after = ctx->ev_a;
+        ctx->lanes[l]->profiling = ctx->profiling;
+    }
+    // profiling pass: one lane after the other, so that the per-kernel times are those of the kernels alone
+    int r = for_each_lane(ctx, lanes, !ctx->profiling, [&](int l) {
+        return solve_batch(ctx->lanes[l], out + ctx->split_first[l], nullptr);
+    });
+    for (int l = 0; l < lanes; ++l) {
+        ctx->lanes[l]->start_after = nullptr;
+        if (r == VILBA_OK) CK(cudaStreamWaitEvent(ctx->stream, ctx->lanes[l]->ev_done, 0), "wait lane");
+    }
+    if (r != VILBA_OK) return r;
+    CK(cudaEventRecord(ctx->ev_b, ctx->stream), "event");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b), "elapsed");
+    const int n = ctx->split_first[lanes];
+    for (int i = 0; i < n; ++i) out[i].solve_ms = ms;  // device time from the first kernel of any lane to the last
+    return VILBA_OK;
+}
+
+int download_split(vilba_ctx* ctx, vilba_result* out) {
+    if (!ctx->split) return download_batch(ctx, out);
+    return for_each_lane(ctx, ctx->split, true, [&](int l) { return download_batch(ctx->lanes[l], out + ctx->split_first[l]); });
 }
 
 }  // namespace
@@ -932,6 +1034,7 @@ void vilba_destroy(vilba_ctx* ctx) {
     ctx->pinned.release();
     ctx->pinned_out.release();
     ctx->pinned_small.release();
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -945,6 +1048,7 @@ const char* vilba_last_error(const vilba_ctx* ctx) { return ctx ? ctx->err.c_str
 
 int vilba_window_upload(vilba_ctx* ctx, const vilba_window* win) {
     if (!ctx) return VILBA_ERR_ARG;
+    ctx->split = 0;
     return upload_batch(ctx, 1, win);
 }
 
@@ -966,19 +1070,23 @@ int vilba_window_download(vilba_ctx* ctx, vilba_result* out) {
 
 int vilba_batch_upload(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win) {
     if (!ctx) return VILBA_ERR_ARG;
-    return upload_batch(ctx, n_windows, win);
+    return upload_split(ctx, n_windows, win);
 }
 
+int vilba_batch_groups(const vilba_ctx* ctx) { return ctx ? std::max(1, ctx->split) : 0; }
+
+static int resident_count(const vilba_ctx* ctx) { return ctx->split ? ctx->split_first[ctx->split] : ctx->n_win; }
+
 int vilba_batch_solve_resident(vilba_ctx* ctx, int32_t n_windows, vilba_result* out) {
-    if (!ctx || !out || n_windows != ctx->n_win) return VILBA_ERR_ARG;
-    int r = solve_batch(ctx, out, nullptr);
+    if (!ctx || !out || n_windows != resident_count(ctx)) return VILBA_ERR_ARG;
+    int r = solve_split(ctx, out);
     for (int i = 0; i < n_windows; ++i) out[i].status = r;
     return r;
 }
 
 int vilba_batch_download(vilba_ctx* ctx, int32_t n_windows, vilba_result* out) {
-    if (!ctx || !out || n_windows != ctx->n_win) return VILBA_ERR_ARG;
-    return download_batch(ctx, out);
+    if (!ctx || !out || n_windows != resident_count(ctx)) return VILBA_ERR_ARG;
+    return download_split(ctx, out);
 }
 
 // ---- one large window sharded by map point over the GPUs of a node (BASELINE config 4) ----
@@ -1053,6 +1161,7 @@ int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, c
         out->status = VILBA_ABORTED;
         return VILBA_ABORTED;
     }
+    ctx->split = 0;
     int r = upload_batch(ctx, 1, win);
     if (r == VILBA_OK) r = solve_batch(ctx, out, stop_flag);
     if (r == VILBA_OK) r = download_batch(ctx, out);
@@ -1067,45 +1176,34 @@ int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, c
 int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win, vilba_result* out) {
     if (!ctx || n_windows < 0 || (n_windows && (!win || !out))) return VILBA_ERR_ARG;
     if (n_windows == 0) return VILBA_OK;
-    const int chunk = ctx->max_batch;
-    const int n_chunks = (n_windows + chunk - 1) / chunk;
-    auto run_chunk = [&](vilba_ctx* c, int ci) {
-        const int b = ci * chunk, nb = std::min(chunk, (int)n_windows - b);
-        int r = upload_batch(c, nb, win + b);
-        if (r == VILBA_OK) r = solve_batch(c, out + b, nullptr);
-        if (r == VILBA_OK) r = download_batch(c, out + b);
-        for (int i = 0; i < nb; ++i) out[b + i].status = r;
-        return r;
-    };
-    if (n_chunks == 1) return run_chunk(ctx, 0);
-    const int lanes = std::max(1, std::min(ctx->n_lanes, n_chunks));
-    while ((int)ctx->lanes.size() < lanes) {
-        vilba_ctx* sub = vilba_create(ctx->device, &ctx->prm);
-        if (!sub) {
-            ctx->err = "could not create a batch lane";
-            return VILBA_ERR_CUDA;
-        }
-        sub->max_batch = ctx->max_batch;
-        ctx->lanes.push_back(sub);
-    }
-    std::vector<int> status(lanes, VILBA_OK);
-    std::vector<std::thread> th;
-    for (int l = 0; l < lanes; ++l)
-        th.emplace_back([&, l]() {
-            for (int ci = l; ci < n_chunks; ci += lanes) {
-                const int r = run_chunk(ctx->lanes[l], ci);
-                if (r < 0) status[l] = r;
-            }
-        });
-    for (auto& t : th) t.join();
+    // at most max_batch * lanes windows are resident at a time; within such a round the lanes run concurrently
+    // (upload, solve and download of one lane overlap the others')
+    const int round = ctx->max_batch * std::max(1, ctx->n_lanes);
     int worst = VILBA_OK;
-    for (int l = 0; l < lanes; ++l) {
-        add_stats(ctx->stats, ctx->lanes[l]->stats);
-        std::memset(&ctx->lanes[l]->stats, 0, sizeof(vilba_stats));
-        if (status[l] < 0) {
-            worst = status[l];
-            ctx->err = ctx->lanes[l]->err;
+    for (int b = 0; b < n_windows; b += round) {
+        const int nb = std::min(round, (int)n_windows - b);
+        std::vector<int> first;
+        const int lanes = plan_split(ctx, nb, first);
+        int r;
+        if (lanes == 1) {
+            r = upload_batch(ctx, nb, win + b);
+            if (r == VILBA_OK) r = solve_batch(ctx, out + b, nullptr);
+            if (r == VILBA_OK) r = download_batch(ctx, out + b);
+        } else {
+            r = ensure_lanes(ctx, lanes);
+            ctx->split = 0;
+            if (r == VILBA_OK)
+                r = for_each_lane(ctx, lanes, true, [&](int l) {
+                    vilba_ctx* c = ctx->lanes[l];
+                    const int f = b + first[l], n = first[l + 1] - first[l];
+                    int q = upload_batch(c, n, win + f);
+                    if (q == VILBA_OK) q = solve_batch(c, out + f, nullptr);
+                    if (q == VILBA_OK) q = download_batch(c, out + f);
+                    return q;
+                });
         }
+        for (int i = 0; i < nb; ++i) out[b + i].status = r;
+        if (r != VILBA_OK && worst >= 0) worst = r;
     }
     return worst;
 }

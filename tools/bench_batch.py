@@ -16,13 +16,13 @@ ctx = api.Context(0)
 prof = os.environ.get("BATCH_PROFILE", "0") == "1"
 for n in sizes:
     wins = [base[i % len(base)] for i in range(n)]
-    if n <= api.max_batch():
+    if n <= min(api.max_batch(), int(os.environ.get("VILBA_MAX_BATCH", "64"))):
         ctx.upload_batch(wins)
         ctx.solve_batch_resident()
         rs = ctx.solve_batch_resident()
         iters = sum(len(r.trace) for r in rs)
         ms = rs[0].solve_ms
-        print(f"resident batch n={n} {name}: {ms:.2f} ms device -> {iters/ms*1e3:.0f} LM iters/s, {n/ms*1e3:.1f} windows/s", flush=True)
+        print(f"resident batch n={n} ({ctx.batch_groups()} lanes) {name}: {ms:.2f} ms device -> {iters/ms*1e3:.0f} LM iters/s, {n/ms*1e3:.1f} windows/s", flush=True)
         if prof:
             ctx.reset_stats()
             ctx.set_profiling(True)
@@ -31,9 +31,13 @@ for n in sizes:
             ctx.set_profiling(False)
             print(f"   per launch: linearize {1e3*s.linearize_ms/max(1,s.linearize_launches):.1f} us x{s.linearize_launches}, "
                   f"schur {1e3*s.schur_ms/max(1,s.schur_launches):.1f} us, chol {1e3*s.solve_ms/max(1,s.solve_launches):.1f} us x{s.solve_launches}", flush=True)
-    ctx.local_ba_batch(wins)  # warm-up: lanes, graphs, arenas
+    prep = ctx.prepare(wins)  # caller-owned host buffers, reused
+    prep.run()  # warm-up: lanes, graphs, arenas
+    prep.run()
     t0 = time.perf_counter()
-    rs = ctx.local_ba_batch(wins)
-    dt = time.perf_counter() - t0
-    iters = sum(len(r.trace) for r in rs)
+    reps = 3
+    for _ in range(reps):
+        prep.run()
+    dt = (time.perf_counter() - t0) / reps
+    iters = sum(len(r.trace) for r in prep.collect())
     print(f"e2e batch n={n} {name}: {dt*1e3:.1f} ms -> {n/dt:.1f} windows/s, {iters/dt:.0f} LM iters/s (host buffers)", flush=True)
