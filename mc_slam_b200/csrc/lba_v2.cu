@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
             const bool have = e < e1i;
             bool to_pose = false;
             int blk = -1;
-            double Jp[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, wgt = 0.0, wr0 = 0.0, wr1 = 0.0;
+            // contributions of this edge to its key-frame's [P,Phi] block: 21 upper entries + 6 rhs entries
+            double ctr[kAccStride];
+#pragma unroll
+            for (int i = 0; i < kAccStride; ++i) ctr[i] = 0.0;
             if (have) {
                 const MonoObs o = load_obs(w.obs, e);
                 double* Wp = w.W + 18 * (size_t)e;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                     V3 Paux, Pc;
                     mono_error(w, cam, Pw, o, r0, r1, Paux, Pc);
                     const double is2 = (double)o.is2;
-                    wgt = is2;
+                    double wgt = is2;
                     if (o.robust) {
                         double rho0, rho1;
                         huber(r0 * (is2 * r0) + r1 * (is2 * r1), w.huber_mono, rho0, rho1);
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                     const double iz = 1.0 / Pc.z;  // see mono_error: one reciprocal for the six divisions by z
                     const double ja = w.fx * iz, jb = (-(Pc.x * iz) * w.fx) * iz;
                     const double jc = w.fy * iz, jd = (-(Pc.y * iz) * w.fy) * iz;
+                    // J_l (2x3, w.r.t. the point) and F (2x3, w.r.t. dPhi); the pose Jacobian is J_p = [-J_l | F]
                     const double l00 = -(ja * Rcw.a00 + jb * Rcw.a20), l01 = -(ja * Rcw.a01 + jb * Rcw.a21),
                                  l02 = -(ja * Rcw.a02 + jb * Rcw.a22);
                     const double l10 = -(jc * Rcw.a10 + jd * Rcw.a20), l11 = -(jc * Rcw.a11 + jd * Rcw.a21),
@@ -235,25 +239,40 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
                                  f02 = -(ja * HR.a02 + jb * HR.a22);
                     const double f10 = -(jc * HR.a10 + jd * HR.a20), f11 = -(jc * HR.a11 + jd * HR.a21),
                                  f12 = -(jc * HR.a12 + jd * HR.a22);
-                    const double Jl[2][3] = {{l00, l01, l02}, {l10, l11, l12}};
-                    Jp[0][0] = -l00, Jp[0][1] = -l01, Jp[0][2] = -l02, Jp[0][3] = f00, Jp[0][4] = f01, Jp[0][5] = f02;
-                    Jp[1][0] = -l10, Jp[1][1] = -l11, Jp[1][2] = -l12, Jp[1][3] = f10, Jp[1][4] = f11, Jp[1][5] = f12;
-                    hxx += wgt * (l00 * l00 + l10 * l10);
-                    hxy += wgt * (l00 * l01 + l10 * l11);
-                    hxz += wgt * (l00 * l02 + l10 * l12);
-                    hyy += wgt * (l01 * l01 + l11 * l11);
-                    hyz += wgt * (l01 * l02 + l11 * l12);
-                    hzz += wgt * (l02 * l02 + l12 * l12);
-                    wr0 = -wgt * r0, wr1 = -wgt * r1;
-                    bx += l00 * wr0 + l10 * wr1;
-                    by += l01 * wr0 + l11 * wr1;
-                    bz += l02 * wr0 + l12 * wr1;
+                    // Because J_p = [-J_l | F], every block of the edge's quadratic form is one of three products:
+                    //   A = J_l^T w J_l (H_ll part, = top-left of H_pp, = -rows 0..2 of H_pl),
+                    //   B = F^T w J_l   (rows 3..5 of H_pl, = -top-right of H_pp transposed),  C = F^T w F.
+                    const double m00 = wgt * l00, m01 = wgt * l01, m02 = wgt * l02;  // w J_l
+                    const double m10 = wgt * l10, m11 = wgt * l11, m12 = wgt * l12;
+                    const double axx = l00 * m00 + l10 * m10, axy = l00 * m01 + l10 * m11, axz = l00 * m02 + l10 * m12;
+                    const double ayy = l01 * m01 + l11 * m11, ayz = l01 * m02 + l11 * m12, azz = l02 * m02 + l12 * m12;
+                    hxx += axx, hxy += axy, hxz += axz, hyy += ayy, hyz += ayz, hzz += azz;
+                    const double wr0 = -wgt * r0, wr1 = -wgt * r1;
+                    const double ebx = l00 * wr0 + l10 * wr1, eby = l01 * wr0 + l11 * wr1, ebz = l02 * wr0 + l12 * wr1;
+                    bx += ebx, by += eby, bz += ebz;
                     if (blk >= 0) {
-#pragma unroll
-                        for (int r = 0; r < 6; ++r)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c)
-                                Wp[3 * r + c] = wgt * (Jp[0][r] * Jl[0][c] + Jp[1][r] * Jl[1][c]);
+                        const double b00 = f00 * m00 + f10 * m10, b01 = f00 * m01 + f10 * m11, b02 = f00 * m02 + f10 * m12;
+                        const double b10 = f01 * m00 + f11 * m10, b11 = f01 * m01 + f11 * m11, b12 = f01 * m02 + f11 * m12;
+                        const double b20 = f02 * m00 + f12 * m10, b21 = f02 * m01 + f12 * m11, b22 = f02 * m02 + f12 * m12;
+                        const double g00 = wgt * f00, g01 = wgt * f01, g02 = wgt * f02;  // w F
+                        const double g10 = wgt * f10, g11 = wgt * f11, g12 = wgt * f12;
+                        // H_pl block (6x3): rows [P] = -A, rows [Phi] = B
+                        Wp[0] = -axx, Wp[1] = -axy, Wp[2] = -axz;
+                        Wp[3] = -axy, Wp[4] = -ayy, Wp[5] = -ayz;
+                        Wp[6] = -axz, Wp[7] = -ayz, Wp[8] = -azz;
+                        Wp[9] = b00, Wp[10] = b01, Wp[11] = b02;
+                        Wp[12] = b10, Wp[13] = b11, Wp[14] = b12;
+                        Wp[15] = b20, Wp[16] = b21, Wp[17] = b22;
+                        // upper triangle of J_p^T w J_p, row-major: [A | -B^T ; . | C]
+                        ctr[0] = axx, ctr[1] = axy, ctr[2] = axz, ctr[3] = -b00, ctr[4] = -b10, ctr[5] = -b20;
+                        ctr[6] = ayy, ctr[7] = ayz, ctr[8] = -b01, ctr[9] = -b11, ctr[10] = -b21;
+                        ctr[11] = azz, ctr[12] = -b02, ctr[13] = -b12, ctr[14] = -b22;
+                        ctr[15] = f00 * g00 + f10 * g10, ctr[16] = f00 * g01 + f10 * g11, ctr[17] = f00 * g02 + f10 * g12;
+                        ctr[18] = f01 * g01 + f11 * g11, ctr[19] = f01 * g02 + f11 * g12;
+                        ctr[20] = f02 * g02 + f12 * g12;
+                        // rhs: J_p^T (-w r) = [-b_l part | F^T (-w r)]
+                        ctr[21] = -ebx, ctr[22] = -eby, ctr[23] = -ebz;
+                        ctr[24] = f00 * wr0 + f10 * wr1, ctr[25] = f01 * wr0 + f11 * wr1, ctr[26] = f02 * wr0 + f12 * wr1;
                         wrote_w = true;
                         to_pose = true;
                     }
@@ -262,21 +281,6 @@ __global__ void __launch_bounds__(kPointThreads, 2) linearize_v2_kernel(const De
 #pragma unroll
                     for (int i = 0; i < 18; ++i) Wp[i] = 0.0;
                 }
-            }
-            // contributions of this edge to its key-frame's [P,Phi] block: 21 upper entries + 6 rhs entries
-            double ctr[kAccStride];
-            {
-                int idx = 0;
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                    for (int c = r; c < 6; ++c) {
-                        ctr[idx] = wgt * (Jp[0][r] * Jp[0][c] + Jp[1][r] * Jp[1][c]);
-                        ++idx;
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 6; ++r) ctr[21 + r] = Jp[0][r] * wr0 + Jp[1][r] * wr1;
             }
 #pragma unroll 1
             for (int ph = 0; ph < 4; ++ph) {
