@@ -174,6 +174,7 @@ struct LaunchDims {
     int sp_grid;          // ... and the points into this many subsets (= partial sums per window)
     int sp_tile_pts;      // map points per shared-memory tile
     int chol_cluster;     // CTAs of the Cholesky cluster
+    int chol_big_tiles;   // > 0: whole-GPU blocked Cholesky (chol_big.cu) with this many 64-column steps, instead of the cluster kernel
     int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
     size_t smem_point;    // dynamic shared memory of update_eval / flags
     size_t smem_lin;      // ... of linearize_v2
@@ -190,6 +191,8 @@ size_t schur_tile_hdr_words(int P, int tile_pts);
 size_t schur_partial_doubles(int n_free);
 bool chol_has_stage(int n_cap);
 int chol_block_size(int n_cap);
+cudaError_t configure_chol_big(int n_cap);
+cudaError_t launch_chol_big(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels
 
 cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);

@@ -187,6 +187,7 @@ struct vilba_ctx {
     size_t in_total = 0, out_total = 0, lm_base = 0, out_region = 0;  // arena: [in | out | lm array | work]
     LaunchDims dims;
     int chol_cluster = 8;
+    int chol_big_above = 640;        // env VILBA_CHOL_BIG_ABOVE: reduced systems larger than this use chol_big.cu
     bool schur_gather_only = false;  // env VILBA_SCHUR=gather (ablation)
     int sp_grid_cap = 74;            // env VILBA_SP_GRID: point subsets per window of the tile-scan Schur kernel
     int sp_sets = 0;                 // env VILBA_SP_SETS: block-pair subsets (0 = automatic)
@@ -592,6 +593,8 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
         ctx->dims.smem_lin = linearize_smem_bytes(ctx->cap_K, ctx->cap_nf);
         ctx->dims.smem_chol = chol_smem_bytes(ctx->cap_n);
         ctx->dims.chol_nb = chol_block_size(ctx->cap_n);
+        // large reduced systems: blocked Cholesky over the whole GPU (chol_big.cu); small ones: one cluster per window
+        ctx->dims.chol_big_tiles = (ctx->cap_n > ctx->chol_big_above) ? (ctx->cap_n + 63) / 64 : 0;
         if (const char* e = std::getenv("VILBA_CHOL_NB")) ctx->dims.chol_nb = (std::atoi(e) == 16) ? 16 : ctx->dims.chol_nb;
         if (ctx->dims.smem_lin > 227 * 1024 || ctx->dims.smem_chol > 227 * 1024) {
             ctx->err = "window too large for the shared-memory stages";
@@ -996,6 +999,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     ctx->dims.chol_nb = 32;
     if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VILBA_CHOL_BIG_ABOVE")) ctx->chol_big_above = std::atoi(e);
     if (const char* e = std::getenv("VILBA_SCHUR")) ctx->schur_gather_only = std::strcmp(e, "gather") == 0;
     if (const char* e = std::getenv("VILBA_SP_GRID")) ctx->sp_grid_cap = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_SP_SETS")) ctx->sp_sets = std::max(1, std::atoi(e));
