@@ -20,9 +20,16 @@ namespace vilba {
 
 constexpr int kBT = 64;        // tile edge
 constexpr int kBTP = kBT + 1;  // padded shared-memory stride
+constexpr int kXS = kBT + 8;   // stride of the row-per-column buffer of trsm (2-way conflicts at most)
 
 __device__ __forceinline__ int big_tiles(int n) { return (n + kBT - 1) / kBT; }
 
+// The kernels keep their loops rolled on purpose: fully unrolled register-resident variants of potrf / trsm were
+// measured 3x slower -- 4 k instructions of straight-line code executed once by two warps are bound by
+// instruction fetch.
+
+// diagonal tile: 256 threads, 4 per row; the pivot's reciprocal square root is computed redundantly by every
+// thread (no publication step): two barriers per column
 __global__ void __launch_bounds__(256) bigchol_potrf_kernel(const DevWindow* __restrict__ wp, int k) {
     const DevWindow w = wp[blockIdx.y];
     if (w.lm->phase != PH_TRIAL) return;
@@ -30,99 +37,98 @@ __global__ void __launch_bounds__(256) bigchol_potrf_kernel(const DevWindow* __r
     if (k >= big_tiles(n)) return;
     const int k0 = k * kBT, nb = min(kBT, n - k0);
     __shared__ double T[kBT][kBTP];
-    __shared__ double s_inv;
-    __shared__ int s_fail;
     double* A = w.S;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_fail = 0;
-    for (int idx = tid; idx < kBT * kBT; idx += blockDim.x) {
+    // a warp = 32 consecutive rows with the same column phase q: T[row][c] is conflict-free, T[c][j] a broadcast
+    const int tid = threadIdx.x, row = (tid & 31) + 32 * ((tid >> 5) & 1), q = tid >> 6;
+    bool fail = false;
+#pragma unroll 4
+    for (int idx = tid; idx < kBT * kBT; idx += 256) {
         const int c = idx / kBT, i = idx - kBT * c;  // consecutive threads walk down a column: coalesced
         T[i][c] = (i < nb && c < nb && i >= c) ? A[(size_t)(k0 + c) * ld + k0 + i] : 0.0;
     }
-    __syncthreads();
+    double l_prev = 0.0;  // L(row, j - 1): stored one column late, when nobody reads the old column any more
     for (int j = 0; j < nb; ++j) {
-        if (tid == 0) {
-            double d = T[j][j];
-            if (!(d > 0.0)) {
-                s_fail = 1;
-                d = 1.0;
-            }
-            d = sqrt(d);
-            T[j][j] = d;
-            s_inv = 1.0 / d;
+        __syncthreads();  // the updates of column j - 1 are complete
+        if (j > 0 && row >= j - 1 && q == 0) T[row][j - 1] = l_prev;
+        double d = T[j][j];
+        if (!(d > 0.0)) {
+            fail = true;
+            d = 1.0;
         }
-        __syncthreads();
-        if (tid > j && tid < nb) T[tid][j] *= s_inv;
-        __syncthreads();
-        // trailing update of the tile: T(i,c) -= L(i,j) L(c,j), j < c <= i
-        const int rem = nb - j - 1;
-        for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
-            const int ci = idx / rem, ii = idx - rem * ci;
-            const int c = j + 1 + ci, i = j + 1 + ii;
-            if (i >= c) T[i][c] -= T[i][j] * T[c][j];
+        const double inv = rsqrt(d);
+        // L(j,j) = sqrt(d), L(i,j) = a(i,j) / sqrt(d); L(c,j) of the other rows is recomputed from the old a(c,j)
+        const double lij = (row > j) ? T[row][j] * inv : d * inv;
+        if (row > j) {
+#pragma unroll 4
+            for (int c = j + 1 + q; c <= row; c += 4) T[row][c] = fma(-lij, T[c][j] * inv, T[row][c]);
         }
-        __syncthreads();
+        l_prev = lij;
     }
-    for (int idx = tid; idx < kBT * kBT; idx += blockDim.x) {
+    __syncthreads();
+    if (nb > 0 && row >= nb - 1 && row < kBT && q == 0) T[row][nb - 1] = l_prev;
+    __syncthreads();
+#pragma unroll 4
+    for (int idx = tid; idx < kBT * kBT; idx += 256) {
         const int c = idx / kBT, i = idx - kBT * c;
         if (i < nb && c < nb && i >= c) A[(size_t)(k0 + c) * ld + k0 + i] = T[i][c];
     }
-    if (tid == 0 && s_fail) w.lm->chol_fail = 1;
+    if (tid < nb) w.cdinv[k0 + tid] = 1.0 / T[tid][tid];  // for the triangular solves
+    if (fail && tid == 0) w.lm->chol_fail = 1;
 }
 
-// rows [k0 + 64, n) of the panel and the rhs row (index n): x L_kk^T = a, one thread per row
-__global__ void __launch_bounds__(128) bigchol_trsm_kernel(const DevWindow* __restrict__ wp, int k) {
+// rows [k0 + 64, n) of the panel and the rhs row (index n): x L_kk^T = a.  64 rows per CTA, 4 threads per row
+// (one warp = 8 rows), the rows live in shared memory; right-looking: once x_c is final the rest of the row is
+// updated, split over the 4 threads of the row, ordered by __syncwarp
+__global__ void __launch_bounds__(256) bigchol_trsm_kernel(const DevWindow* __restrict__ wp, int k) {
     const DevWindow w = wp[blockIdx.y];
     if (w.lm->phase != PH_TRIAL) return;
     const int n = w.n, ld = w.lds;
     if (k >= big_tiles(n)) return;
     const int k0 = k * kBT, nb = min(kBT, n - k0);
-    const int row0 = k0 + kBT;  // first panel row (may be >= n: then only the rhs row is left)
+    const int row0 = k0 + kBT;              // first panel row (may be >= n: then only the rhs row is left)
     const int rows = max(0, n - row0) + 1;  // + rhs
-    if ((int)(blockIdx.x * blockDim.x) >= rows) return;
-    __shared__ double L[kBT][kBTP];  // L_kk padded with the identity
-    __shared__ double dinv[kBT];
+    const int r_base = blockIdx.x * kBT;
+    if (r_base >= rows) return;
+    extern __shared__ double trsm_sm[];
+    double (*L)[kBTP] = reinterpret_cast<double (*)[kBTP]>(trsm_sm);              // L_kk padded with the identity
+    double (*X)[kXS] = reinterpret_cast<double (*)[kXS]>(trsm_sm + kBT * kBTP);  // X[c][row]
+    double* dinv = trsm_sm + kBT * kBTP + kBT * kXS;
     double* A = w.S;
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < kBT * kBT; idx += blockDim.x) {
+#pragma unroll 4
+    for (int idx = tid; idx < kBT * kBT; idx += 256) {
         const int c = idx / kBT, i = idx - kBT * c;
         double v = (i == c) ? 1.0 : 0.0;
         if (i < nb && c < nb && i >= c) v = A[(size_t)(k0 + c) * ld + k0 + i];
         L[i][c] = v;
+        const int r = r_base + i;  // row i of this CTA, column c
+        double xv = 0.0;
+        if (r < rows && c < nb) xv = (r == rows - 1) ? w.bs[k0 + c] : A[(size_t)(k0 + c) * ld + row0 + r];
+        X[c][i] = xv;
+    }
+    if (tid < kBT) dinv[tid] = tid < nb ? w.cdinv[k0 + tid] : 1.0;
+    __syncthreads();
+    // one warp = 8 rows x 4 column phases, phase-major: the 8 lanes of a phase read 64 contiguous bytes
+    const int lane = tid & 31, rl = (tid >> 5) * 8 + (lane & 7), q = lane >> 3;
+    for (int c = 0; c < nb; ++c) {
+        const double xc = X[c][rl] * dinv[c];
+        __syncwarp();
+        if (q == 0) X[c][rl] = xc;
+#pragma unroll 4
+        for (int m = c + 1 + q; m < nb; m += 4) X[m][rl] = fma(-xc, L[m][c], X[m][rl]);
+        __syncwarp();
     }
     __syncthreads();
-    if (tid < kBT) dinv[tid] = 1.0 / L[tid][tid];
-    __syncthreads();
-    const int r = blockIdx.x * blockDim.x + tid;
-    if (r >= rows) return;
-    const bool is_rhs = (r == rows - 1);
-    const int gi = row0 + r;  // global row (unused for the rhs)
-    double x[kBT];
-#pragma unroll
-    for (int c = 0; c < kBT; ++c) {
-        double v = 0.0;
-        if (c < nb) v = is_rhs ? w.bs[k0 + c] : A[(size_t)(k0 + c) * ld + gi];
-        x[c] = v;
-    }
-#pragma unroll
-    for (int c = 0; c < kBT; ++c) {
-        double s0 = x[c], s1 = 0.0;
-#pragma unroll
-        for (int m = 0; m + 1 < c; m += 2) {
-            s0 = fma(-x[m], L[c][m], s0);
-            s1 = fma(-x[m + 1], L[c][m + 1], s1);
+#pragma unroll 4
+    for (int idx = tid; idx < kBT * kBT; idx += 256) {
+        const int c = idx / kBT, i = idx - kBT * c;
+        const int r = r_base + i;
+        if (r < rows && c < nb) {
+            if (r == rows - 1)
+                w.x[k0 + c] = X[c][i];  // y_k = forward-substituted right-hand side
+            else
+                A[(size_t)(k0 + c) * ld + row0 + r] = X[c][i];
         }
-        if (c & 1) s0 = fma(-x[c - 1], L[c][c - 1], s0);
-        x[c] = (s0 + s1) * dinv[c];
-    }
-    if (is_rhs) {
-#pragma unroll
-        for (int c = 0; c < kBT; ++c)
-            if (c < nb) w.x[k0 + c] = x[c];  // y_k = forward-substituted right-hand side
-    } else {
-#pragma unroll
-        for (int c = 0; c < kBT; ++c)
-            if (c < nb) A[(size_t)(k0 + c) * ld + gi] = x[c];
     }
 }
 
@@ -150,11 +156,21 @@ __global__ void __launch_bounds__(256) bigchol_update_kernel(const DevWindow* __
         const int I0 = (k + 1 + Ip) * kBT, J0 = (k + 1 + Jp) * kBT;
         const int ni = min(kBT, n - I0), nj = min(kBT, n - J0);
         __syncthreads();
-        for (int idx = tid; idx < kBT * kBT; idx += blockDim.x) {
+#pragma unroll 8
+        for (int idx = tid; idx < kBT * kBT; idx += 256) {
             const int c = idx / kBT, i = idx - kBT * c;
             PI[i][c] = (i < ni) ? A[(size_t)(k0 + c) * ld + I0 + i] : 0.0;
             PJ[i][c] = (i < nj) ? A[(size_t)(k0 + c) * ld + J0 + i] : 0.0;
         }
+        // the tile of C, fetched while the products are formed
+        double cv[4][4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int i = tx + 16 * a, j = ty + 16 * b;
+                cv[a][b] = (i < ni && j < nj && I0 + i >= J0 + j) ? A[(size_t)(J0 + j) * ld + I0 + i] : 0.0;
+            }
         __syncthreads();
         double acc[4][4];
 #pragma unroll
@@ -179,14 +195,17 @@ __global__ void __launch_bounds__(256) bigchol_update_kernel(const DevWindow* __
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int i = tx + 16 * a;
-                if (i < ni && j < nj && I0 + i >= J0 + j) A[(size_t)(J0 + j) * ld + I0 + i] -= acc[a][b];
+                if (i < ni && j < nj && I0 + i >= J0 + j) A[(size_t)(J0 + j) * ld + I0 + i] = cv[a][b] - acc[a][b];
             }
         }
         if (Ip == Jp && tid < nj) {  // rhs rows of this diagonal tile
-            double s = 0.0;
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll 8
-            for (int c = 0; c < kBT; ++c) s = fma(PJ[tid][c], w.x[k0 + c], s);
-            w.bs[J0 + tid] -= s;
+            for (int c = 0; c < kBT; c += 2) {
+                s0 = fma(PJ[tid][c], w.x[k0 + c], s0);
+                s1 = fma(PJ[tid][c + 1], w.x[k0 + c + 1], s1);
+            }
+            w.bs[J0 + tid] -= s0 + s1;
         }
     }
 }
@@ -205,24 +224,30 @@ __global__ void __launch_bounds__(1024) bigchol_backsub_kernel(const DevWindow* 
     const int ntile = big_tiles(n);
     for (int k = ntile - 1; k >= 0; --k) {
         const int k0 = k * kBT, nb = min(kBT, n - k0), below = k0 + kBT;
-        for (int idx = tid; idx < kBT * kBT; idx += blockDim.x) {
+#pragma unroll 4
+        for (int idx = tid; idx < kBT * kBT; idx += 1024) {
             const int c = idx / kBT, i = idx - kBT * c;
             Lt[i * kBTP + c] = (i < nb && c < nb && i >= c) ? A[(size_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
         }
         // s_c = y_c - sum_{i >= below} L(i, k0 + c) x_i : one warp per column, lanes along the (contiguous) rows
         for (int c = warp; c < nb; c += nwarp) {
             const double* col = A + (size_t)(k0 + c) * ld;
-            double s = 0.0;
-            for (int i = below + lane; i < n; i += 32) s = fma(col[i], xs[i], s);
-            s = warp_sum(s);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int i = below + lane;
+            for (; i + 96 < n; i += 128) {
+                const double a0 = col[i], a1 = col[i + 32], a2 = col[i + 64], a3 = col[i + 96];
+                s0 = fma(a0, xs[i], s0), s1 = fma(a1, xs[i + 32], s1), s2 = fma(a2, xs[i + 64], s2), s3 = fma(a3, xs[i + 96], s3);
+            }
+            for (; i < n; i += 32) s0 = fma(col[i], xs[i], s0);
+            const double s = warp_sum((s0 + s1) + (s2 + s3));
             if (lane == 0) sv[c] = w.x[k0 + c] - s;
         }
         __syncthreads();
         if (warp == 0) {  // 64 x 64 triangular solve with L_kk^T: lanes own columns c and c + 32
             double s0 = lane < nb ? sv[lane] : 0.0, s1 = lane + 32 < nb ? sv[lane + 32] : 0.0;
+            const double di0 = lane < nb ? w.cdinv[k0 + lane] : 1.0, di1 = lane + 32 < nb ? w.cdinv[k0 + lane + 32] : 1.0;
             for (int m = nb - 1; m >= 0; --m) {
-                const double sm_ = __shfl_sync(0xffffffffu, m < 32 ? s0 : s1, m & 31);
-                const double xm = sm_ / Lt[m * kBTP + m];
+                const double xm = __shfl_sync(0xffffffffu, m < 32 ? s0 * di0 : s1 * di1, m & 31);
                 if (lane == (m & 31)) {
                     if (m < 32) s0 = xm; else s1 = xm;
                 }
@@ -240,9 +265,12 @@ __global__ void __launch_bounds__(1024) bigchol_backsub_kernel(const DevWindow* 
 size_t chol_big_backsub_smem(int n_cap) { return sizeof(double) * ((size_t)((n_cap + 1) & ~1) + kBT * kBTP + kBT); }
 
 constexpr size_t kUpdateSmem = sizeof(double) * 2 * kBT * kBTP;
+constexpr size_t kTrsmSmem = sizeof(double) * (kBT * kBTP + kBT * kXS + kBT);
 
 cudaError_t configure_chol_big(int n_cap) {
     cudaError_t e = cudaFuncSetAttribute(bigchol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(bigchol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(bigchol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_big_backsub_smem(n_cap));
 }
@@ -252,7 +280,7 @@ cudaError_t launch_chol_big(cudaStream_t s, const DevWindow* wp, const LaunchDim
     for (int k = 0; k < ntile; ++k) {
         bigchol_potrf_kernel<<<dim3(1, d.n_windows), 256, 0, s>>>(wp, k);
         const int rows = (ntile - k - 1) * kBT + 1;
-        bigchol_trsm_kernel<<<dim3((rows + 127) / 128, d.n_windows), 128, 0, s>>>(wp, k);
+        bigchol_trsm_kernel<<<dim3((rows + 63) / 64, d.n_windows), 256, kTrsmSmem, s>>>(wp, k);
         const int T = ntile - k - 1;
         if (T > 0) {
             const int npair = T * (T + 1) / 2;
