@@ -173,6 +173,7 @@ struct LaunchDims {
     int sp_sets;          // the key-frame block pairs are cut into this many contiguous subsets (CTAs) ...
     int sp_grid;          // ... and the points into this many subsets (= partial sums per window)
     int sp_tile_pts;      // map points per shared-memory tile
+    int sp_pair_lanes;    // 1: one lane per block pair (36 accumulators), one CTA covers all pairs of the window
     int chol_cluster;     // CTAs of the Cholesky cluster
     int chol_big_tiles;   // > 0: whole-GPU blocked Cholesky (chol_big.cu) with this many 64-column steps, instead of the cluster kernel
     int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
@@ -187,6 +188,8 @@ size_t chol_smem_bytes(int n);
 bool schur_tile_fits(int K, int n_free);   // the tile-scan Schur kernel handles windows of <= 32 key-frames
 size_t schur_tile_smem_bytes(int max_K, int tile_pts);
 size_t schur_tile_rec_doubles(int P);
+int schur_pair_lanes(int n_free);                 // lanes (= threads) of the lane-per-pair tile kernel
+size_t schur_pair_partial_doubles(int n_free);    // size of one of its partial sums
 size_t schur_tile_hdr_words(int P, int tile_pts);
 size_t schur_partial_doubles(int n_free);
 bool chol_has_stage(int n_cap);

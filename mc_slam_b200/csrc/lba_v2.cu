@@ -766,6 +766,195 @@ __global__ void __launch_bounds__(512) schur_tile_kernel(const DevWindow* __rest
     }
 }
 
+// Variant with ONE LANE PER BLOCK PAIR: the lane keeps the whole 6x6 block (36 accumulators) in registers, so the
+// per-hit bookkeeping (mask, popcounts, addresses, record loads) is paid once per 108 + 54 FMAs instead of once per
+// 18 + 9, and the 36 chains are independent.  One CTA covers all pairs of a window (W is read once); the points are
+// split over gridDim.x CTAs.  Balance: pairs of close key-frames are hit by many more points than distant ones, so a
+// pair at distance d gets R(d) = 3, 2 or 1 lanes that share its hits (point l of a tile goes to lane l mod R); the lanes
+// are ordered by distance, so the lanes of a warp have similar hit counts.
+__host__ __device__ static inline size_t schur_pair_partial_doubles_dev(int nf);
+__host__ __device__ static inline int ts_replicas(int d, int nf) {
+    const int x = 100 * d / (nf + 1);  // distance in percent of the window length
+    return x < 14 ? 3 : (x < 41 ? 2 : 1);
+}
+__host__ __device__ static inline int ts_pair_lanes(int nf) {
+    int lanes = 0;
+    for (int d = 0; d < nf; ++d) lanes += (nf - d) * ts_replicas(d, nf);
+    return lanes;
+}
+// lane -> (a, b, replica k of R); returns false beyond the last lane
+__device__ __forceinline__ bool ts_lane_to_pair(int lane, int nf, int& a, int& b, int& k, int& R) {
+    int off = 0;
+    for (int d = 0; d < nf; ++d) {
+        R = ts_replicas(d, nf);
+        const int cnt = (nf - d) * R;
+        if (lane < off + cnt) {
+            const int idx = lane - off;
+            a = idx / R;
+            k = idx - a * R;
+            b = a + d;
+            return true;
+        }
+        off += cnt;
+    }
+    return false;
+}
+__device__ __forceinline__ int ts_pair_first_lane(int a, int b, int nf) {
+    const int d = b - a;
+    int off = 0;
+    for (int dd = 0; dd < d; ++dd) off += (nf - dd) * ts_replicas(dd, nf);
+    return off + a * ts_replicas(d, nf);
+}
+__host__ __device__ static inline size_t schur_pair_partial_doubles_dev(int nf) { return (size_t)ts_pair_lanes(nf) * 36 + (size_t)nf * 6 * 3; }
+int schur_pair_lanes(int n_free) { return ts_pair_lanes(n_free); }
+size_t schur_pair_partial_doubles(int n_free) { return schur_pair_partial_doubles_dev(n_free); }
+
+__global__ void __launch_bounds__(384) schur_tile_pair_kernel(const DevWindow* __restrict__ wp, int tile_pts) {
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
+    if (w.lm->phase != PH_TRIAL) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar[2];
+    const TsLayout L = ts_layout(w.K, tile_pts);
+    const int psub = blockIdx.x, npsub = gridDim.x;
+    const int nf = w.n_free;
+    int a = 0, b = 0, rk = 0, R = 1;
+    const bool live = ts_lane_to_pair(threadIdx.x, nf, a, b, rk, R);
+    int ka = 0, kb = 0;
+    if (live) ka = w.blk_kf[a], kb = w.blk_kf[b];
+    const bool diag = live && a == b;
+    const unsigned below_a = (1u << ka) - 1u, below_b = (1u << kb) - 1u;
+    // points l of a tile with l mod R == rk
+    const unsigned mine = R == 1 ? 0xffffffffu : (R == 2 ? (0x55555555u << rk) : (0x49249249u << rk));
+    double acc[36];
+    double rb[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+    const int ntile = (w.P + tile_pts - 1) / tile_pts;
+    const int g_begin = (int)((long long)ntile * psub / npsub), g_end = (int)((long long)ntile * (psub + 1) / npsub);
+    const int nt = g_end - g_begin;
+    const bool leader = threadIdx.x == 0;
+    if (leader) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int g, int b2, int e_lo, int e_hi) {
+        unsigned char* buf = smem_raw + (size_t)b2 * L.buf_bytes;
+        const int p0 = g * tile_pts, np = min(tile_pts, w.P - p0);
+        const unsigned wbytes = 144u * (unsigned)(e_hi - e_lo), rbytes = 8u * kTsRecDoubles * (unsigned)np, hbytes = 4u * kTsHdrWords;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_expect_tx(&bar[b2], wbytes + rbytes + hbytes);
+        if (wbytes) tma_load_1d(buf + L.w, w.W + 18 * (size_t)e_lo, wbytes, &bar[b2]);
+        tma_load_1d(buf + L.rec, w.ts_rec + (size_t)kTsRecDoubles * p0, rbytes, &bar[b2]);
+        tma_load_1d(buf + L.hdr, w.ts_hdr + (size_t)kTsHdrWords * g, hbytes, &bar[b2]);
+    };
+    auto tile_edges = [&](int t, int& e_lo, int& e_hi) {
+        e_lo = e_hi = 0;
+        if (leader && t < nt) {
+            const int p0 = (g_begin + t) * tile_pts;
+            e_lo = w.pt_obs_begin[p0];
+            e_hi = w.pt_obs_begin[min(p0 + tile_pts, w.P)];
+        }
+    };
+    int e_lo_n, e_hi_n, e_lo_nn, e_hi_nn;
+    tile_edges(0, e_lo_n, e_hi_n);
+    if (leader && nt > 0) issue(g_begin, 0, e_lo_n, e_hi_n);
+    tile_edges(1, e_lo_n, e_hi_n);
+    for (int t = 0; t < nt; ++t) {
+        if (leader && t + 1 < nt) issue(g_begin + t + 1, (t + 1) & 1, e_lo_n, e_hi_n);
+        tile_edges(t + 2, e_lo_nn, e_hi_nn);
+        const unsigned char* buf = smem_raw + (size_t)(t & 1) * L.buf_bytes;
+        const double* bW = reinterpret_cast<const double*>(buf + L.w);
+        const double* bRec = reinterpret_cast<const double*>(buf + L.rec);
+        const unsigned* colmask = reinterpret_cast<const unsigned*>(buf + L.hdr);
+        mbar_wait(&bar[t & 1], (unsigned)((t >> 1) & 1));
+        unsigned hits = live ? (colmask[ka] & colmask[kb] & mine) : 0u;
+#ifdef VILBA_TS_ABLATE
+        if (w.dbg_flags & 2) hits = 0u;
+#endif
+        while (hits) {
+            const int l = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const double* d = bRec + kTsRecDoubles * l;
+            const uint2 mk = *reinterpret_cast<const uint2*>(d + 9);
+            const unsigned eb = *reinterpret_cast<const unsigned*>(d + 10);
+            const double* Wi = bW + 18 * (eb + __popc(mk.x & below_a));
+            const double2* Wj = reinterpret_cast<const double2*>(bW + 18 * (eb + __popc(mk.x & below_b)));
+            const double dxx = d[0], dxy = d[1], dxz = d[2], dyy = d[3], dyz = d[4], dzz = d[5];
+            double wj[18];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const double2 v = Wj[i];
+                wj[2 * i] = v.x, wj[2 * i + 1] = v.y;
+            }
+            const double b0 = d[6], b1 = d[7], b2 = d[8];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {  // row r of W_i D^-1 (BDinv, block_solver.hpp:407), then row r of the block
+                const double w0 = Wi[3 * r], w1 = Wi[3 * r + 1], w2 = Wi[3 * r + 2];
+                const double y0 = fma(dxz, w2, fma(dxy, w1, dxx * w0));
+                const double y1 = fma(dyz, w2, fma(dyy, w1, dxy * w0));
+                const double y2 = fma(dzz, w2, fma(dyz, w1, dxz * w0));
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    acc[6 * r + c] = fma(y2, wj[3 * c + 2], fma(y1, wj[3 * c + 1], fma(y0, wj[3 * c], acc[6 * r + c])));
+                if (diag) rb[r] = fma(w2, b2, fma(w1, b1, fma(w0, b0, rb[r])));  // rhs: b_s(a) -= W_a (D^-1 b_l)
+            }
+        }
+        e_lo_n = e_lo_nn, e_hi_n = e_hi_nn;
+        __syncthreads();  // tile t consumed: its buffer may be refilled
+    }
+    if (live) {
+        double* part = w.schur_partial + (size_t)psub * schur_pair_partial_doubles_dev(nf);
+        double* dst = part + (size_t)threadIdx.x * 36;
+#pragma unroll
+        for (int i = 0; i < 36; ++i) dst[i] = acc[i];
+        if (diag) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) part[(size_t)ts_pair_lanes(nf) * 36 + (6 * a + r) * 3 + rk] = rb[r];
+        }
+    }
+}
+
+// finish for the lane-per-pair layout: S = H_pp + lambda I - sum over point subsets and replicas (fixed order)
+__global__ void __launch_bounds__(256) schur_finish_pair_kernel(const DevWindow* __restrict__ wp, int point_ctas) {
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
+    if (w.lm->phase != PH_TRIAL) return;
+    const int n = w.n, nf = w.n_free;
+    const double lambda = w.lm->lambda;
+    const size_t accN = schur_pair_partial_doubles_dev(nf);
+    const size_t rhs0 = (size_t)ts_pair_lanes(nf) * 36;
+    const size_t total = (size_t)n * n + n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const bool is_rhs = i >= (size_t)n * n;
+        int gr, gc;
+        if (is_rhs) {
+            gr = gc = (int)(i - (size_t)n * n);
+        } else {
+            gr = (int)(i / n);
+            gc = (int)(i - (size_t)gr * n);
+            if (gr > gc) continue;
+        }
+        const int a = gr / 15, b = gc / 15, rr = gr - 15 * a, cc = gc - 15 * b;
+        const int pr = pose6_index(rr), pc = pose6_index(cc);
+        double v = !w.shard_owner ? 0.0 : (is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc]);
+        if (!is_rhs && gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
+        if (pr >= 0 && (is_rhs || pc >= 0)) {
+            const int R = ts_replicas(b - a, nf);
+            const size_t off = is_rhs ? rhs0 + (size_t)(6 * a + pr) * 3 : (size_t)ts_pair_first_lane(a, b, nf) * 36 + 6 * pr + pc;
+            const size_t step = is_rhs ? 1 : 36;
+            double sum = 0.0;
+            for (int c = 0; c < point_ctas; ++c)
+                for (int k = 0; k < R; ++k) sum += w.schur_partial[(size_t)c * accN + off + step * k];
+            v -= sum;
+        }
+        if (is_rhs)
+            w.bs_w[gr] = v;
+        else
+            w.S_w[(size_t)gr * w.lds + gc] = v;
+    }
+}
+
 // S = H_pp + lambda I - sum of the CTA partials (fixed order), b_s = b_p - sum; upper triangle only
 __global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __restrict__ wp, int point_ctas) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
@@ -820,6 +1009,8 @@ cudaError_t configure_kernels(const LaunchDims& d) {
     if (d.smem_sp > 0) {
         e = cudaFuncSetAttribute(schur_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_sp);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(schur_tile_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_sp);
+        if (e != cudaSuccess) return e;
     }
     e = configure_point_kernels(d);
     if (e != cudaSuccess) return e;
@@ -851,9 +1042,15 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
     if (d.sp_warps > 0) {
         schur_rec_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_tile_pts);
-        schur_tile_kernel<<<dim3(d.sp_grid * d.sp_sets, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_sets, d.sp_tile_pts);
+        if (d.sp_pair_lanes)
+            schur_tile_pair_kernel<<<dim3(d.sp_grid, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_tile_pts);
+        else
+            schur_tile_kernel<<<dim3(d.sp_grid * d.sp_sets, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_sets, d.sp_tile_pts);
         if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;
-        schur_finish_kernel<<<dim3(d.assemble_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_grid);
+        if (d.sp_pair_lanes)
+            schur_finish_pair_kernel<<<dim3(d.assemble_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_grid);
+        else
+            schur_finish_kernel<<<dim3(d.assemble_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_grid);
     } else {
         schur_prep_kernel<<<dim3(d.point_grid, d.n_windows), 256, 0, s>>>(wp);
         if (probe && (e = cudaEventRecord(probe[6], s)) != cudaSuccess) return e;

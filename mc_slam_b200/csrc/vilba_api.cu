@@ -142,7 +142,7 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bo
     L.imu_slot = take(sizeof(double) * 930 * NI);
     L.mono_sum = take(sizeof(double) * 27 * n_free);
     L.Y = take(gather ? sizeof(double) * 24 * E : 0);
-    L.schur_partial = take(sizeof(double) * schur_partial_doubles((int)n_free) * (size_t)sp_ctas);
+    L.schur_partial = take(sizeof(double) * std::max(schur_partial_doubles((int)n_free), schur_pair_partial_doubles((int)n_free)) * (size_t)sp_ctas);
     L.ts_rec = take(gather ? 0 : sizeof(double) * schur_tile_rec_doubles((int)P) + 256);
     L.ts_hdr = take(gather ? 0 : sizeof(unsigned) * schur_tile_hdr_words((int)P, tile_pts));
     const size_t lds = (n + 3) & ~(size_t)3;
@@ -190,6 +190,7 @@ struct vilba_ctx {
     int chol_big_above = 640;        // env VILBA_CHOL_BIG_ABOVE: reduced systems larger than this use chol_big.cu
     bool schur_gather_only = false;  // env VILBA_SCHUR=gather (ablation)
     int sp_grid_cap = 74;            // env VILBA_SP_GRID: point subsets per window of the tile-scan Schur kernel
+    int sp_pair_lanes = 0;           // env VILBA_SP_PAIR=1: lane-per-pair variant of the tile-scan Schur kernel
     int sp_sets = 0;                 // env VILBA_SP_SETS: block-pair subsets (0 = automatic)
     int cap_K = 0, cap_nf = 0, cap_n = 0;  // capacities the shared-memory sizes were configured for
     std::vector<GraphEntry> graphs;        // one captured LM slot per launch geometry
@@ -323,6 +324,13 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
         d.sp_sets = (max_groups + 5 * d.sp_warps - 1) / (5 * d.sp_warps);  // every group must have its lanes
         d.sp_grid = std::max(1, std::min(ctx->sp_grid_cap, 2 * sm / (d.sp_sets * n_win)));
         d.sp_tile_pts = std::max(4, std::min(32, (int)(46 * 1024 / (144 * (size_t)std::min(32, max_K)))));
+        d.sp_pair_lanes = 0;
+        if (ctx->sp_pair_lanes && schur_pair_lanes(max_nf) <= 384) {
+            d.sp_pair_lanes = 1;
+            d.sp_sets = 1;
+            d.sp_warps = (schur_pair_lanes(max_nf) + 31) / 32;
+            d.sp_grid = std::max(1, std::min(ctx->sp_grid_cap, 2 * sm / n_win));
+        }
         if (const char* e = std::getenv("VILBA_SP_PSUB")) d.sp_grid = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("VILBA_SP_TILE")) d.sp_tile_pts = std::max(2, std::min(d.sp_tile_pts, std::atoi(e)));
         d.smem_sp = schur_tile_smem_bytes(max_K, d.sp_tile_pts);
@@ -1003,6 +1011,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     if (const char* e = std::getenv("VILBA_SCHUR")) ctx->schur_gather_only = std::strcmp(e, "gather") == 0;
     if (const char* e = std::getenv("VILBA_SP_GRID")) ctx->sp_grid_cap = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_SP_SETS")) ctx->sp_sets = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("VILBA_SP_PAIR")) ctx->sp_pair_lanes = std::atoi(e);
     if (const char* e = std::getenv("VILBA_BATCH_LANES")) ctx->n_lanes = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_MAX_BATCH")) ctx->max_batch = std::max(1, std::min(kMaxBatch, std::atoi(e)));
     ctx->dims = choose_dims(ctx, 1, 0, 0, 0);
