@@ -256,6 +256,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()  # nvidia-smi needs ~1 s to start: sample from the warm-up on (same load), through the timed region
     ctx.upload_batch(wins)
+    groups = max(1, ctx.batch_groups())  # concurrent lanes: one launch covers nw / groups windows
     t_warm = time.perf_counter()
     while True:  # at least W warm-up steps and ~1.5 s of load so that the clock samples cover the timed region
         timed_resident(ctx, W)
@@ -324,7 +325,6 @@ def main():
     if rank == 0:
         peak, peak_src = _peaks()
         n_red = 15 * wins[0].n_free
-        groups = max(1, ctx.batch_groups())  # concurrent lanes: one launch covers nw / groups windows
         b_lin = sum(algorithmic_bytes_linearize(w) for w in wins) / groups
         lin_us = 1e3 * stp.linearize_ms / max(1, stp.linearize_launches)
         chol_us = 1e3 * stp.solve_ms / max(1, stp.solve_launches)
