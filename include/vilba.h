@@ -192,7 +192,7 @@ int vilba_window_download(vilba_ctx* ctx, vilba_result* out);
 
 /* The same for a resident batch of independent windows: every kernel is launched once per lane for all the
  * lane's windows (one grid row per window) and each window runs its own device-side LM controller; batches of
- * 16 or more windows are split over up to 3 lanes (env VILBA_BATCH_LANES) that run concurrently.
+ * 16 or more windows are split over up to 4 lanes (env VILBA_BATCH_LANES) that run concurrently.
  * out[i].solve_ms is the device time of the whole batch (first kernel of any lane to the last). */
 int vilba_max_batch(void);
 /* lanes (concurrent sub-batches, each with its own streams) the resident batch is split over: a launch of any

@@ -209,12 +209,13 @@ struct vilba_ctx {
     SlotComm slot_comm;
     // a large batch is split over a few sub-contexts ("lanes": own streams, arena, graphs, one host thread each)
     // whose batched solves run concurrently: the kernels are latency-bound, a second and third stream fill the SMs
+    int batch_total_hint = 0;            // lane: windows of the whole batch (all lanes), for the Cholesky cluster size
     int split = 0;                       // lanes the resident batch is split over (0: it lives in this context)
     std::vector<int> split_first;        // first window of every lane (+ end)
     cudaEvent_t start_after = nullptr;   // lane: event of the parent stream the solve starts after
     cudaEvent_t ev_done = nullptr;       // lane: recorded behind the last kernel of a solve
     std::vector<vilba_ctx*> lanes;  // sub-contexts of vilba_local_ba_batch: chunks of the batch are pipelined over them
-    int n_lanes = 3;                // env VILBA_BATCH_LANES
+    int n_lanes = 4;                // env VILBA_BATCH_LANES
     std::vector<cudaEvent_t> probes;  // 8 events per profiled slot
     size_t probes_used = 0;
     double dbg_ms[4] = {0, 0, 0, 0};
@@ -338,7 +339,8 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
     // Cholesky: as many CTAs per window as the machine has to spare (one 8-CTA cluster for a single window,
     // smaller clusters when many windows share the SMs: a CTA is more efficient the fewer partners it waits for)
     int cl = 1;
-    while (2 * cl <= ctx->chol_cluster && 2 * cl * n_win <= sm) cl *= 2;
+    const int n_all = std::max(n_win, ctx->batch_total_hint);  // windows of all concurrent lanes share the SMs
+    while (2 * cl <= ctx->chol_cluster && 2 * cl * n_all <= sm) cl *= 2;
     d.chol_cluster = n_win == 1 ? ctx->chol_cluster : cl;
     return d;
 }
@@ -919,6 +921,7 @@ int upload_split(vilba_ctx* ctx, int n, const vilba_window* wins) {
     int r = ensure_lanes(ctx, lanes);
     if (r != VILBA_OK) return r;
     r = for_each_lane(ctx, lanes, true, [&](int l) {
+        ctx->lanes[l]->batch_total_hint = n;
         return upload_batch(ctx->lanes[l], ctx->split_first[l + 1] - ctx->split_first[l], wins + ctx->split_first[l]);
     });
     if (r == VILBA_OK) ctx->split = lanes;
@@ -1208,6 +1211,7 @@ int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* 
             if (r == VILBA_OK)
                 r = for_each_lane(ctx, lanes, true, [&](int l) {
                     vilba_ctx* c = ctx->lanes[l];
+                    c->batch_total_hint = nb;
                     const int f = b + first[l], n = first[l + 1] - first[l];
                     int q = upload_batch(c, n, win + f);
                     if (q == VILBA_OK) q = solve_batch(c, out + f, nullptr);
