@@ -740,7 +740,7 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
                 CK(cudaGraphLaunch(exec, s), "graph launch");
             else
                 CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, probe_take(ctx), comm), "slot");
-            stt.kernel_launches += kKernelsPerSlot + (ctx->dims.sp_warps > 0 ? 1 : 0);
+            stt.kernel_launches += kernels_per_slot(ctx->dims);
         }
         int r = read_lm(ctx, lm, stop_flag);
         if (r != VILBA_OK) return r;

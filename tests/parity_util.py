@@ -21,6 +21,6 @@ def compare(r, o, w, chi_rtol=1e-6, state_atol=1e-5):
     assert np.abs(r.kf_state[:, 6:10] - o.kf_state[:, 6:10]).max() <= state_atol  # R (quaternion)
     assert np.abs(r.kf_state[:, 16:22] - o.kf_state[:, 16:22]).max() <= state_atol  # dbg, dba
     assert np.array_equal(r.kf_state[:, 10:16], w.kf_state[:, 10:16])  # base biases untouched
-    assert np.abs(r.pt_xyz - o.pt_xyz).max() <= state_atol
+    assert np.abs(r.pt_xyz - o.pt_xyz).max(initial=0.0) <= state_atol
     assert np.array_equal(r.obs_outlier, o.obs_outlier)
     assert np.allclose(r.obs_chi2, o.obs_chi2, rtol=1e-6, atol=1e-9)

@@ -188,3 +188,56 @@ def test_local_ba_c4_large_window(ctx, oracle):
     assert w.n_obs > 550_000 and 15 * w.n_free == 1485
     r, o = ctx.local_ba(w), oracle.local_ba(w)
     _compare(r, o, w)
+
+
+# ---- edge cases of the window shape ------------------------------------------------------------------
+def _subset_points(w, keep):
+    """Window with only the map points `keep` (boolean mask), observations re-packed."""
+    import dataclasses
+    keep = np.asarray(keep, bool)
+    cnt = np.diff(w.pt_obs_begin)
+    emask = np.repeat(keep, cnt)
+    begin = np.zeros(int(keep.sum()) + 1, np.int32)
+    np.cumsum(cnt[keep], out=begin[1:])
+    return dataclasses.replace(w, pt_xyz=w.pt_xyz[keep].copy(), pt_obs_begin=begin, obs_kf=w.obs_kf[emask].copy(),
+                               obs_uv=w.obs_uv[emask].copy(), obs_inv_sigma2=w.obs_inv_sigma2[emask].copy(), truth={})
+
+
+def test_window_without_map_points_is_imu_only(ctx, oracle):
+    """No mono edges at all: the reduced system is the IMU chain alone (no Schur step to speak of)."""
+    w = synth.make_config("small")
+    w0 = _subset_points(w, np.zeros(w.n_pts, bool))
+    assert w0.n_pts == 0 and w0.n_obs == 0
+    _compare(ctx.local_ba(w0), oracle.local_ba(w0), w0)
+
+
+def test_few_points_and_ragged_batch(ctx, oracle):
+    """A handful of points (most tiles / CTAs have nothing to do) next to ordinary windows in one batch."""
+    w = synth.make_config("small")
+    keep = np.zeros(w.n_pts, bool)
+    keep[[0, 7, 8, 150, 299]] = True
+    wins = [_subset_points(w, keep), synth.make_config("tiny", window_index=2), _subset_points(w, np.zeros(w.n_pts, bool)),
+            synth.make_config("small", window_index=5)]
+    for wi, r in zip(wins, ctx.local_ba_batch(wins)):
+        _compare(r, oracle.local_ba(wi), wi)
+
+
+@pytest.mark.parametrize("n_kf", [32, 33])
+def test_window_at_the_tile_scan_limit(ctx, oracle, n_kf):
+    """32 key-frames is the largest window the tile-scan Schur kernel takes (32-bit observer masks); 33 switches
+    to the gather over pair lists.  Both against the oracle."""
+    w = synth.make_window(n_kf=n_kf, n_pts=600, mean_run=6.0, seed=synth.SEED_BASE + 77)
+    assert w.n_kf == n_kf
+    _compare(ctx.local_ba(w), oracle.local_ba(w), w)
+
+
+def test_lane_per_pair_schur_variant(oracle, monkeypatch):
+    """The experimental lane-per-pair tile kernel (VILBA_SP_PAIR=1) solves the same windows."""
+    monkeypatch.setenv("VILBA_SP_PAIR", "1")
+    from mc_slam_b200 import api
+    c = api.Context(0)
+    try:
+        for w in (synth.make_config("small", n_fixed_extra=1), synth.make_config("c1", window_index=2)):
+            _compare(c.local_ba(w), oracle.local_ba(w), w)
+    finally:
+        c.close()
