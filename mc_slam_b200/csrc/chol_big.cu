@@ -13,6 +13,7 @@
 // controller then rejects the trial, optimization_algorithm_levenberg.cpp:126-127) and is replaced by 1 so
 // that everything stays finite.  Every kernel returns at once unless its window is in the TRIAL phase.
 #include <algorithm>
+#include <cstdlib>
 
 #include "lba_common.cuh"
 
@@ -30,7 +31,8 @@ __device__ __forceinline__ int big_tiles(int n) { return (n + kBT - 1) / kBT; }
 
 // diagonal tile: 256 threads, 4 per row; the pivot's reciprocal square root is computed redundantly by every
 // thread (no publication step): two barriers per column
-__global__ void __launch_bounds__(256) bigchol_potrf_kernel(const DevWindow* __restrict__ wp, int k) {
+template <int TPR>  // threads per row of the tile
+__global__ void __launch_bounds__(64 * TPR) bigchol_potrf_kernel(const DevWindow* __restrict__ wp, int k) {
     const DevWindow w = wp[blockIdx.y];
     if (w.lm->phase != PH_TRIAL) return;
     const int n = w.n, ld = w.lds;
@@ -40,27 +42,46 @@ __global__ void __launch_bounds__(256) bigchol_potrf_kernel(const DevWindow* __r
     double* A = w.S;
     // a warp = 32 consecutive rows with the same column phase q: T[row][c] is conflict-free, T[c][j] a broadcast
     const int tid = threadIdx.x, row = (tid & 31) + 32 * ((tid >> 5) & 1), q = tid >> 6;
-    bool fail = false;
 #pragma unroll 4
-    for (int idx = tid; idx < kBT * kBT; idx += 256) {
+    for (int idx = tid; idx < kBT * kBT; idx += 64 * TPR) {
         const int c = idx / kBT, i = idx - kBT * c;  // consecutive threads walk down a column: coalesced
         T[i][c] = (i < nb && c < nb && i >= c) ? A[(size_t)(k0 + c) * ld + k0 + i] : 0.0;
     }
+    __shared__ double s_rs[2];  // 1 / sqrt(pivot) of the current column, published one column ahead
+    __shared__ int s_bad;
+    if (tid == 0) {
+        s_bad = 0;
+        double d0 = nb > 0 ? A[(size_t)k0 * ld + k0] : 1.0;
+        if (!(d0 > 0.0)) {
+            s_bad = 1;
+            d0 = 1.0;
+            T[0][0] = 1.0;  // (this thread loaded T[0][0] itself)
+        }
+        s_rs[0] = rsqrt(d0);
+    }
     double l_prev = 0.0;  // L(row, j - 1): stored one column late, when nobody reads the old column any more
     for (int j = 0; j < nb; ++j) {
-        __syncthreads();  // the updates of column j - 1 are complete
+        __syncthreads();  // the updates of column j - 1 are complete, s_rs[j & 1] is published
         if (j > 0 && row >= j - 1 && q == 0) T[row][j - 1] = l_prev;
-        double d = T[j][j];
-        if (!(d > 0.0)) {
-            fail = true;
-            d = 1.0;
-        }
-        const double inv = rsqrt(d);
-        // L(j,j) = sqrt(d), L(i,j) = a(i,j) / sqrt(d); L(c,j) of the other rows is recomputed from the old a(c,j)
-        const double lij = (row > j) ? T[row][j] * inv : d * inv;
+        const double inv = s_rs[j & 1];
+        // L(j,j) = sqrt(d) = d / sqrt(d), L(i,j) = a(i,j) / sqrt(d); L(c,j) of the other rows is recomputed from a(c,j)
+        const double lij = T[row][j] * inv;
         if (row > j) {
+            // the owner of the next pivot finishes it first and publishes its reciprocal square root, so that the
+            // rsqrt chain runs beside the other threads' updates instead of in front of everybody's next column
+            if (row == j + 1 && q == 0 && j + 1 < nb) {
+                double dn = fma(-lij, T[j + 1][j] * inv, T[j + 1][j + 1]);
+                T[j + 1][j + 1] = dn;
+                if (!(dn > 0.0)) {
+                    s_bad = 1;
+                    dn = 1.0;
+                    T[j + 1][j + 1] = 1.0;
+                }
+                s_rs[(j + 1) & 1] = rsqrt(dn);
+            } else {
 #pragma unroll 4
-            for (int c = j + 1 + q; c <= row; c += 4) T[row][c] = fma(-lij, T[c][j] * inv, T[row][c]);
+                for (int c = j + 1 + q; c <= row; c += TPR) T[row][c] = fma(-lij, T[c][j] * inv, T[row][c]);
+            }
         }
         l_prev = lij;
     }
@@ -68,12 +89,12 @@ __global__ void __launch_bounds__(256) bigchol_potrf_kernel(const DevWindow* __r
     if (nb > 0 && row >= nb - 1 && row < kBT && q == 0) T[row][nb - 1] = l_prev;
     __syncthreads();
 #pragma unroll 4
-    for (int idx = tid; idx < kBT * kBT; idx += 256) {
+    for (int idx = tid; idx < kBT * kBT; idx += 64 * TPR) {
         const int c = idx / kBT, i = idx - kBT * c;
         if (i < nb && c < nb && i >= c) A[(size_t)(k0 + c) * ld + k0 + i] = T[i][c];
     }
     if (tid < nb) w.cdinv[k0 + tid] = 1.0 / T[tid][tid];  // for the triangular solves
-    if (fail && tid == 0) w.lm->chol_fail = 1;
+    if (tid == 0 && s_bad) w.lm->chol_fail = 1;
 }
 
 // rows [k0 + 64, n) of the panel and the rhs row (index n): x L_kk^T = a.  64 rows per CTA, 4 threads per row
@@ -278,7 +299,15 @@ cudaError_t configure_chol_big(int n_cap) {
 cudaError_t launch_chol_big(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
     const int ntile = d.chol_big_tiles;
     for (int k = 0; k < ntile; ++k) {
-        bigchol_potrf_kernel<<<dim3(1, d.n_windows), 256, 0, s>>>(wp, k);
+        static const int tpr = std::getenv("VILBA_POTRF_TPR") ? std::atoi(std::getenv("VILBA_POTRF_TPR")) : 8;
+        if (tpr == 2)
+            bigchol_potrf_kernel<2><<<dim3(1, d.n_windows), 128, 0, s>>>(wp, k);
+        else if (tpr == 8)
+            bigchol_potrf_kernel<8><<<dim3(1, d.n_windows), 512, 0, s>>>(wp, k);
+        else if (tpr == 16)
+            bigchol_potrf_kernel<16><<<dim3(1, d.n_windows), 1024, 0, s>>>(wp, k);
+        else
+            bigchol_potrf_kernel<4><<<dim3(1, d.n_windows), 256, 0, s>>>(wp, k);
         const int rows = (ntile - k - 1) * kBT + 1;
         bigchol_trsm_kernel<<<dim3((rows + 63) / 64, d.n_windows), 256, kTrsmSmem, s>>>(wp, k);
         const int T = ntile - k - 1;
