@@ -370,7 +370,7 @@ def main():
         }
         if single:
             line["single_window"] = single
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
             threads = 1 if nw == 1 else min(host_threads(), nw)
             reps = 3
             val, n_solved, _, _, _ = cpu_throughput(wins[:max(threads, 1)], threads, reps)

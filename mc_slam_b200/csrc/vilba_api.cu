@@ -202,6 +202,7 @@ struct vilba_ctx {
     void* nccl_lib = nullptr;
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_world = 1;
+    bool comm_graph = true;   // the sharded slot (kernels + allreduces) is captured in a CUDA graph too; env VILBA_COMM_GRAPH=0 disables
     ncclResult_t (*p_ncclCommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*p_ncclCommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*p_ncclAllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -696,7 +697,8 @@ int ensure_graph(vilba_ctx* ctx, cudaGraphExec_t* out) {
         }
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
-    cudaError_t e = launch_slot(ctx->stream, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, nullptr);
+    cudaError_t e = launch_slot(ctx->stream, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, nullptr,
+                                ctx->comm ? &ctx->slot_comm : nullptr);  // NCCL collectives are capturable
     cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &g);
     if (fail(ctx, e, "capture slot") || fail(ctx, e2, "end capture")) return VILBA_ERR_CUDA;
     GraphEntry ge;
@@ -724,7 +726,7 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
     if (comm && slot_reduce(ctx, RED_CHI, s) != cudaSuccess) return VILBA_ERR_COMM;
     CK(launch_stage_begin(s, ctx->dwp, ctx->dims, stage, iterations), "stage_begin");
     stt.kernel_launches += 2;
-    const bool graph = ctx->use_graph && !ctx->profiling && !comm;  // the collectives are enqueued between the kernels
+    const bool graph = ctx->use_graph && !ctx->profiling && (!comm || ctx->comm_graph);
     cudaGraphExec_t exec = nullptr;
     if (graph) {
         int r = ensure_graph(ctx, &exec);
@@ -1015,6 +1017,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     if (const char* e = std::getenv("VILBA_SP_GRID")) ctx->sp_grid_cap = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_SP_SETS")) ctx->sp_sets = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_SP_PAIR")) ctx->sp_pair_lanes = std::atoi(e);
+    if (const char* e = std::getenv("VILBA_COMM_GRAPH")) ctx->comm_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("VILBA_BATCH_LANES")) ctx->n_lanes = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_MAX_BATCH")) ctx->max_batch = std::max(1, std::min(kMaxBatch, std::atoi(e)));
     ctx->dims = choose_dims(ctx, 1, 0, 0, 0);
