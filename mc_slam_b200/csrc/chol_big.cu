@@ -79,8 +79,20 @@ __global__ void __launch_bounds__(64 * TPR) bigchol_potrf_kernel(const DevWindow
                 }
                 s_rs[(j + 1) & 1] = rsqrt(dn);
             } else {
-#pragma unroll 4
-                for (int c = j + 1 + q; c <= row; c += TPR) T[row][c] = fma(-lij, T[c][j] * inv, T[row][c]);
+                for (int c0 = j + 1 + q; c0 <= row; c0 += 4 * TPR) {  // chunks of 4: loads first, then stores
+                    double tv[4], cv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c0 + TPR * i;
+                        tv[i] = c <= row ? T[row][c] : 0.0;
+                        cv[i] = c <= row ? T[c][j] : 0.0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c0 + TPR * i;
+                        if (c <= row) T[row][c] = fma(-lij, cv[i] * inv, tv[i]);
+                    }
+                }
             }
         }
         l_prev = lij;
@@ -135,8 +147,21 @@ __global__ void __launch_bounds__(256) bigchol_trsm_kernel(const DevWindow* __re
         const double xc = X[c][rl] * dinv[c];
         __syncwarp();
         if (q == 0) X[c][rl] = xc;
-#pragma unroll 4
-        for (int m = c + 1 + q; m < nb; m += 4) X[m][rl] = fma(-xc, L[m][c], X[m][rl]);
+        // chunks of 8 entries: all loads, then all stores
+        for (int m0 = c + 1 + q; m0 < nb; m0 += 32) {
+            double xv[8], lv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + 4 * i;
+                xv[i] = m < nb ? X[m][rl] : 0.0;
+                lv[i] = m < nb ? L[m][c] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + 4 * i;
+                if (m < nb) X[m][rl] = fma(-xc, lv[i], xv[i]);
+            }
+        }
         __syncwarp();
     }
     __syncthreads();
