@@ -689,9 +689,19 @@ int read_lm(vilba_ctx* ctx, std::vector<LmState>& lm, const volatile uint8_t* st
 
 bool stop_requested(const volatile uint8_t* f) { return f && *f; }
 
+// field-wise (the struct has padding bytes, memcmp would compare them)
+bool same_dims(const LaunchDims& a, const LaunchDims& b) {
+    return a.sm_count == b.sm_count && a.n_windows == b.n_windows && a.point_grid == b.point_grid && a.imu_grid == b.imu_grid &&
+           a.gather_grid == b.gather_grid && a.reduce_grid == b.reduce_grid && a.assemble_grid == b.assemble_grid &&
+           a.sp_warps == b.sp_warps && a.sp_sets == b.sp_sets && a.sp_grid == b.sp_grid && a.sp_tile_pts == b.sp_tile_pts &&
+           a.sp_pair_lanes == b.sp_pair_lanes && a.chol_cluster == b.chol_cluster && a.chol_big_tiles == b.chol_big_tiles &&
+           a.chol_nb == b.chol_nb && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.smem_chol == b.smem_chol &&
+           a.smem_sp == b.smem_sp;
+}
+
 int ensure_graph(vilba_ctx* ctx, cudaGraphExec_t* out) {
     for (const GraphEntry& g : ctx->graphs)
-        if (std::memcmp(&g.dims, &ctx->dims, sizeof(LaunchDims)) == 0) {
+        if (same_dims(g.dims, ctx->dims)) {
             *out = g.exec;
             return VILBA_OK;
         }
@@ -1143,6 +1153,7 @@ int vilba_comm_init(vilba_ctx* ctx, const void* unique_id128, int32_t rank, int3
         ctx->err = std::string("ncclCommInitRank: ") + (ctx->p_ncclGetErrorString ? ctx->p_ncclGetErrorString(r) : "?");
         return VILBA_ERR_COMM;
     }
+    drop_graphs(ctx);  // slots captured without the collectives
     ctx->comm_rank = rank, ctx->comm_world = world;
     ctx->slot_comm.self = ctx;
     ctx->slot_comm.reduce = slot_reduce;
