@@ -179,14 +179,16 @@ __global__ void __launch_bounds__(256) bigchol_trsm_kernel(const DevWindow* __re
 }
 
 // trailing tiles (I >= J > k): C_IJ -= P_I P_J^T ; diagonal tiles also b_J -= P_J y_k
-__global__ void __launch_bounds__(256) bigchol_update_kernel(const DevWindow* __restrict__ wp, int k) {
+// part 0: every tile; part 1: only the tiles of block column k + 1 (what the next potrf / trsm need: "look-ahead");
+// part 2: the other tiles (they run on a side stream beside the next step's potrf and trsm)
+__global__ void __launch_bounds__(256) bigchol_update_kernel(const DevWindow* __restrict__ wp, int k, int part) {
     const DevWindow w = wp[blockIdx.y];
     if (w.lm->phase != PH_TRIAL) return;
     const int n = w.n, ld = w.lds;
     const int ntile = big_tiles(n);
     const int T = ntile - k - 1;  // tiles left below / right of tile k
     if (T <= 0) return;
-    const int npair = T * (T + 1) / 2;
+    const int npair = part == 0 ? T * (T + 1) / 2 : (part == 1 ? T : (T - 1) * T / 2);
     extern __shared__ double upd_sm[];
     double (*PI)[kBTP] = reinterpret_cast<double (*)[kBTP]>(upd_sm);
     double (*PJ)[kBTP] = reinterpret_cast<double (*)[kBTP]>(upd_sm + kBT * kBTP);
@@ -194,11 +196,13 @@ __global__ void __launch_bounds__(256) bigchol_update_kernel(const DevWindow* __
     const int k0 = k * kBT;  // tile k is complete here (T > 0): 64 columns
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     for (int pr = blockIdx.x; pr < npair; pr += gridDim.x) {
-        // pr = I' (I' + 1) / 2 + J', 0 <= J' <= I' < T
+        // pr = I' (I' + 1) / 2 + J', 0 <= J' <= I' < T   (part 1: J' = 0; part 2: the triangle without its first column)
         int Ip = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
         while (Ip * (Ip + 1) / 2 > pr) --Ip;
         while ((Ip + 1) * (Ip + 2) / 2 <= pr) ++Ip;
-        const int Jp = pr - Ip * (Ip + 1) / 2;
+        int Jp = pr - Ip * (Ip + 1) / 2;
+        if (part == 1) Ip = pr, Jp = 0;
+        if (part == 2) Ip += 1, Jp += 1;
         const int I0 = (k + 1 + Ip) * kBT, J0 = (k + 1 + Jp) * kBT;
         const int ni = min(kBT, n - I0), nj = min(kBT, n - J0);
         __syncthreads();
@@ -321,26 +325,48 @@ cudaError_t configure_chol_big(int n_cap) {
     return cudaFuncSetAttribute(bigchol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_big_backsub_smem(n_cap));
 }
 
-cudaError_t launch_chol_big(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+cudaError_t launch_chol_big(cudaStream_t s, cudaStream_t side, cudaEvent_t ev_trsm, cudaEvent_t ev_rest, const DevWindow* wp,
+                            const LaunchDims& d) {
     const int ntile = d.chol_big_tiles;
+    static const int tpr = std::getenv("VILBA_POTRF_TPR") ? std::atoi(std::getenv("VILBA_POTRF_TPR")) : 8;
+    static const bool lookahead = !(std::getenv("VILBA_CHOL_LOOKAHEAD") && std::atoi(std::getenv("VILBA_CHOL_LOOKAHEAD")) == 0);
+    cudaError_t e;
+    bool rest_pending = false;
     for (int k = 0; k < ntile; ++k) {
-        static const int tpr = std::getenv("VILBA_POTRF_TPR") ? std::atoi(std::getenv("VILBA_POTRF_TPR")) : 8;
         if (tpr == 2)
             bigchol_potrf_kernel<2><<<dim3(1, d.n_windows), 128, 0, s>>>(wp, k);
-        else if (tpr == 8)
-            bigchol_potrf_kernel<8><<<dim3(1, d.n_windows), 512, 0, s>>>(wp, k);
         else if (tpr == 16)
             bigchol_potrf_kernel<16><<<dim3(1, d.n_windows), 1024, 0, s>>>(wp, k);
-        else
+        else if (tpr == 4)
             bigchol_potrf_kernel<4><<<dim3(1, d.n_windows), 256, 0, s>>>(wp, k);
+        else
+            bigchol_potrf_kernel<8><<<dim3(1, d.n_windows), 512, 0, s>>>(wp, k);
         const int rows = (ntile - k - 1) * kBT + 1;
         bigchol_trsm_kernel<<<dim3((rows + 63) / 64, d.n_windows), 256, kTrsmSmem, s>>>(wp, k);
         const int T = ntile - k - 1;
-        if (T > 0) {
-            const int npair = T * (T + 1) / 2;
-            bigchol_update_kernel<<<dim3(std::min(npair, 4 * d.sm_count), d.n_windows), 256, kUpdateSmem, s>>>(wp, k);
+        if (T <= 0) continue;
+        if (!lookahead) {
+            bigchol_update_kernel<<<dim3(std::min(T * (T + 1) / 2, 4 * d.sm_count), d.n_windows), 256, kUpdateSmem, s>>>(wp, k, 0);
+            continue;
+        }
+        // look-ahead: block column k + 1 on the main stream (the next potrf / trsm wait only for it), the rest of
+        // the trailing matrix on the side stream, beside them
+        if (rest_pending) {  // this step's tiles were last written by the previous step's rest
+            if ((e = cudaStreamWaitEvent(s, ev_rest, 0)) != cudaSuccess) return e;
+            rest_pending = false;
+        }
+        if (T > 1) {
+            if ((e = cudaEventRecord(ev_trsm, s)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(side, ev_trsm, 0)) != cudaSuccess) return e;
+        }
+        bigchol_update_kernel<<<dim3(T, d.n_windows), 256, kUpdateSmem, s>>>(wp, k, 1);
+        if (T > 1) {
+            bigchol_update_kernel<<<dim3(std::min((T - 1) * T / 2, 4 * d.sm_count), d.n_windows), 256, kUpdateSmem, side>>>(wp, k, 2);
+            if ((e = cudaEventRecord(ev_rest, side)) != cudaSuccess) return e;
+            rest_pending = true;
         }
     }
+    if (rest_pending && (e = cudaStreamWaitEvent(s, ev_rest, 0)) != cudaSuccess) return e;
     bigchol_backsub_kernel<<<dim3(1, d.n_windows), 1024, chol_big_backsub_smem(d.chol_big_tiles * kBT), s>>>(wp);
     return cudaGetLastError();
 }

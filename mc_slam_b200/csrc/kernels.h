@@ -195,7 +195,8 @@ size_t schur_partial_doubles(int n_free);
 bool chol_has_stage(int n_cap);
 int chol_block_size(int n_cap);
 cudaError_t configure_chol_big(int n_cap);
-cudaError_t launch_chol_big(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_chol_big(cudaStream_t s, cudaStream_t side, cudaEvent_t ev_trsm, cudaEvent_t ev_rest, const DevWindow* wp,
+                            const LaunchDims& d);
 cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels
 
 cudaError_t launch_imu_prepare(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);

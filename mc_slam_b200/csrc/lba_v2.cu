@@ -1058,7 +1058,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     }
     if (comm && (e = comm->reduce(comm->self, RED_S, s)) != cudaSuccess) return e;  // S | b_s = sum of the partial reduced systems
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
-    if ((e = (d.chol_big_tiles > 0 ? launch_chol_big(s, wp, d) : launch_chol_cluster(s, wp, d))) != cudaSuccess) return e;
+    if ((e = (d.chol_big_tiles > 0 ? launch_chol_big(s, side, fork, join, wp, d) : launch_chol_cluster(s, wp, d))) != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;
     if ((e = launch_update_eval_apply(s, wp, d)) != cudaSuccess) return e;
     if (comm && (e = comm->reduce(comm->self, RED_CHI, s)) != cudaSuccess) return e;  // chi2 and the landmark part of the gain scale
