@@ -23,6 +23,7 @@
 #ifndef VILBA_H
 #define VILBA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -241,6 +242,23 @@ int vilba_preintegrate_batch_dev(vilba_ctx* ctx, int32_t n_pairs, int32_t n_samp
                                  const int32_t* sample_begin_dev, const double* gyro_dev,
                                  const double* acc_dev, const double* dt_dev, const double* bg_dev,
                                  const double* ba_dev, double* out_dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Wire / on-disk format of a window (host code, no GPU needed).  The reference has no serialised form of a
+ * window: it re-gathers it from KeyFrame / MapPoint objects on every call (src/Optimizer.cpp:2329-2402).  The
+ * blob is the struct-of-arrays window above made self-describing (256-byte header: magic "VILBAWIN", version,
+ * endianness tag, counts, calibration, payload length and FNV-1a 64 checksum; then the arrays in declaration
+ * order, each padded to 8 bytes), so that windows captured from a patched reference build can be stored, sent to
+ * another process / GPU and replayed through vilba_local_ba.  Layout: mc_slam_b200/csrc/window_blob.cu.
+ *   vilba_window_blob_size   : bytes vilba_window_serialize will write (0 for an invalid window)
+ *   vilba_window_serialize   : writes the blob into buf (capacity >= blob size); *written = its size
+ *   vilba_window_deserialize : zero-copy view: *out points INTO buf (8-byte aligned, must outlive the view);
+ *                              rejects wrong magic / version / endianness, truncation, checksum mismatch and
+ *                              out-of-range indices with VILBA_ERR_ARG
+ * ------------------------------------------------------------------------------------------- */
+size_t vilba_window_blob_size(const vilba_window* win);
+int vilba_window_serialize(const vilba_window* win, void* buf, size_t capacity, size_t* written);
+int vilba_window_deserialize(const void* buf, size_t len, vilba_window* out);
 
 /* ---------------------------------------------------------------------------------------------
  * Introspection for the bench harness

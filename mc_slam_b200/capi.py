@@ -207,6 +207,46 @@ class Window:
     def n_free(self) -> int:
         return int(np.count_nonzero((self.kf_flags & KF_FIXED) == 0))
 
+    # ---- wire / on-disk format (include/vilba.h: vilba_window_serialize / _deserialize) ----------------
+    def to_bytes(self) -> bytes:
+        lib = load_library()
+        cw = self.as_c()
+        n = lib.vilba_window_blob_size(C.byref(cw))
+        if n == 0:
+            raise ValueError("invalid window")
+        buf = np.zeros(n // 8, np.uint64)  # 8-byte aligned
+        written = C.c_size_t(0)
+        st = lib.vilba_window_serialize(C.byref(cw), buf.ctypes.data_as(C.c_void_p), n, C.byref(written))
+        if st != 0 or written.value != n:
+            raise ValueError(f"vilba_window_serialize failed ({st})")
+        return buf.tobytes()
+
+    @staticmethod
+    def from_bytes(blob: bytes) -> "Window":
+        lib = load_library()
+        n = len(blob)
+        buf = np.zeros((n + 7) // 8, np.uint64)
+        C.memmove(buf.ctypes.data, blob, n)
+        cw = CWindow()
+        st = lib.vilba_window_deserialize(buf.ctypes.data_as(C.c_void_p), n, C.byref(cw))
+        if st != 0:
+            raise ValueError(f"vilba_window_deserialize failed ({st}): not a window blob, truncated or corrupt")
+        K, NI, P, E = cw.n_kf, cw.n_imu, cw.n_pts, cw.n_obs
+
+        def arr(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+        return Window(
+            kf_state=arr(cw.kf_state, NS_DOUBLES * K, np.float64), kf_flags=arr(cw.kf_flags, K, np.uint8),
+            kf_id=arr(cw.kf_id, K, np.int64), imu_kf_i=arr(cw.imu_kf_i, NI, np.int32), imu_kf_j=arr(cw.imu_kf_j, NI, np.int32),
+            imu_preint=arr(cw.imu_preint, PREINT_DOUBLES * NI, np.float64), pt_xyz=arr(cw.pt_xyz, 3 * P, np.float64),
+            pt_obs_begin=arr(cw.pt_obs_begin, P + 1, np.int32), obs_kf=arr(cw.obs_kf, E, np.int32),
+            obs_uv=arr(cw.obs_uv, 2 * E, np.float32), obs_inv_sigma2=arr(cw.obs_inv_sigma2, E, np.float32),
+            fx=cw.fx, fy=cw.fy, cx=cw.cx, cy=cw.cy, Rbc=np.array(list(cw.Rbc)), Pbc=np.array(list(cw.Pbc)),
+            gravity=np.array(list(cw.gravity)))
+
     def as_c(self) -> CWindow:
         w = CWindow()
         w.n_kf, w.n_imu, w.n_pts, w.n_obs = self.n_kf, self.n_imu, self.n_pts, self.n_obs
@@ -311,6 +351,9 @@ EXPORTED_SYMBOLS = [  # every symbol include/vilba.h declares
     "vilba_comm_unique_id",
     "vilba_comm_init",
     "vilba_shard_points",
+    "vilba_window_blob_size",
+    "vilba_window_serialize",
+    "vilba_window_deserialize",
     "vilba_preintegrate_batch",
     "vilba_preintegrate_batch_dev",
     "vilba_get_stats",
@@ -369,6 +412,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vilba_comm_init.restype = C.c_int
     lib.vilba_shard_points.argtypes = [C.POINTER(CWindow), C.c_int32, C.c_int32, _c_int32_p, _c_int32_p]
     lib.vilba_shard_points.restype = C.c_int
+    lib.vilba_window_blob_size.argtypes = [C.POINTER(CWindow)]
+    lib.vilba_window_blob_size.restype = C.c_size_t
+    lib.vilba_window_serialize.argtypes = [C.POINTER(CWindow), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.vilba_window_serialize.restype = C.c_int
+    lib.vilba_window_deserialize.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(CWindow)]
+    lib.vilba_window_deserialize.restype = C.c_int
     lib.vilba_preintegrate_batch.argtypes = [
         C.c_void_p, C.c_int32, _c_int32_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
         _c_double_p,
