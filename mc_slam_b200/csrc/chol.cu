@@ -440,9 +440,9 @@ size_t chol_smem_bytes(int n) {
 }
 
 cudaError_t configure_chol(const LaunchDims& d) {
-    cudaError_t e = cudaFuncSetAttribute(chol_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_chol);
+    cudaError_t e = opt_in_max_smem(chol_cluster_kernel<16>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chol_cluster_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_chol);
+    e = opt_in_max_smem(chol_cluster_kernel<32>);
     if (e != cudaSuccess) return e;
     if (d.chol_cluster > 8) {
         e = cudaFuncSetAttribute(chol_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);

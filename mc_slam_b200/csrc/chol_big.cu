@@ -1,4 +1,4 @@
-// chol_big.cu -- reduced camera system of LARGE windows (n > 640, e.g. BASELINE config 4: n = 1485): blocked
+// chol_big.cu -- reduced camera system of LARGE windows (n > 480, e.g. BASELINE config 4: n = 1485): blocked
 // right-looking Cholesky over the whole GPU instead of one thread-block cluster.
 //
 // Replaces LinearSolverEigen::solve (g2o/solvers/linear_solver_eigen.h:94-124: SimplicialLDLT factor + two
@@ -318,11 +318,11 @@ constexpr size_t kUpdateSmem = sizeof(double) * 2 * kBT * kBTP;
 constexpr size_t kTrsmSmem = sizeof(double) * (kBT * kBTP + kBT * kXS + kBT);
 
 cudaError_t configure_chol_big(int n_cap) {
-    cudaError_t e = cudaFuncSetAttribute(bigchol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem);
+    cudaError_t e = opt_in_max_smem(bigchol_update_kernel);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(bigchol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem);
+    e = opt_in_max_smem(bigchol_trsm_kernel);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(bigchol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_big_backsub_smem(n_cap));
+    return opt_in_max_smem(bigchol_backsub_kernel);
 }
 
 cudaError_t launch_chol_big(cudaStream_t s, cudaStream_t side, cudaEvent_t ev_trsm, cudaEvent_t ev_rest, const DevWindow* wp,

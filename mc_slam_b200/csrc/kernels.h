@@ -145,6 +145,20 @@ struct DevWindow {
     int max_trials;
 };
 
+// Opt a kernel in to the largest dynamic shared-memory size the device allows.  The attribute is per FUNCTION and
+// process-wide, not per context: a context configured for small windows must not lower the limit under a context that
+// handles large ones, so every kernel simply gets the maximum (the carve-out still follows the size of each launch).
+template <class F>
+inline cudaError_t opt_in_max_smem(F func) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, func);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
 // ---- K1 ------------------------------------------------------------------------------------------
 size_t preint_smem_bytes(int group);
 cudaError_t launch_preint_batch(cudaStream_t stream, int n_pairs, const int* sample_begin, const double* gyro,

@@ -430,13 +430,13 @@ cudaError_t launch_export(cudaStream_t s, const DevWindow* wp, const LaunchDims&
     return cudaGetLastError();
 }
 cudaError_t configure_point_kernels(const LaunchDims& d) {
-    cudaError_t e = cudaFuncSetAttribute(update_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_point);
+    cudaError_t e = opt_in_max_smem(update_eval_kernel<true>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(update_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_point);
+    e = opt_in_max_smem(update_eval_kernel<false>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(flags_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_point);
+    e = opt_in_max_smem(flags_kernel<true>);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(flags_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_point);
+    return opt_in_max_smem(flags_kernel<false>);
 }
 
 }  // namespace vilba

@@ -1004,12 +1004,12 @@ cudaError_t configure_point_kernels(const LaunchDims& d);
 cudaError_t configure_chol(const LaunchDims& d);
 
 cudaError_t configure_kernels(const LaunchDims& d) {
-    cudaError_t e = cudaFuncSetAttribute(linearize_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_lin);
+    cudaError_t e = opt_in_max_smem(linearize_v2_kernel);
     if (e != cudaSuccess) return e;
     if (d.smem_sp > 0) {
-        e = cudaFuncSetAttribute(schur_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_sp);
+        e = opt_in_max_smem(schur_tile_kernel);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(schur_tile_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_sp);
+        e = opt_in_max_smem(schur_tile_pair_kernel);
         if (e != cudaSuccess) return e;
     }
     e = configure_point_kernels(d);

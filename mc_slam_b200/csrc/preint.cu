@@ -228,8 +228,7 @@ cudaError_t launch_preint_batch(cudaStream_t stream, int n_pairs, const int* sam
     {                                                                                                       \
         const int pairs_per_cta = warps_per_cta * (32 / Gv);                                                \
         const int grid = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;                                     \
-        cudaError_t e = cudaFuncSetAttribute(preint_batch_kernel<Gv>,                                       \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        cudaError_t e = opt_in_max_smem(preint_batch_kernel<Gv>);       \
         if (e != cudaSuccess) return e;                                                                     \
         preint_batch_kernel<Gv><<<grid, kPreintThreads, smem, stream>>>(n_pairs, sample_begin, gyro, acc,   \
                                                                          dt, bg, ba, out, gyr_cov, acc_cov); \

@@ -187,7 +187,8 @@ struct vilba_ctx {
     size_t in_total = 0, out_total = 0, lm_base = 0, out_region = 0;  // arena: [in | out | lm array | work]
     LaunchDims dims;
     int chol_cluster = 8;
-    int chol_big_above = 640;        // env VILBA_CHOL_BIG_ABOVE: reduced systems larger than this use chol_big.cu
+    int chol_big_above = 480;        // env VILBA_CHOL_BIG_ABOVE: reduced systems larger than this use chol_big.cu (the cluster
+                                     // kernel's panel + row stage fit in shared memory up to n = 508)
     bool schur_gather_only = false;  // env VILBA_SCHUR=gather (ablation)
     int sp_grid_cap = 74;            // env VILBA_SP_GRID: point subsets per window of the tile-scan Schur kernel
     int sp_pair_lanes = 0;           // env VILBA_SP_PAIR=1: lane-per-pair variant of the tile-scan Schur kernel
@@ -226,7 +227,12 @@ namespace {
 
 bool fail(vilba_ctx* c, cudaError_t e, const char* what) {
     if (e == cudaSuccess) return false;
-    c->err = std::string(what) + ": " + cudaGetErrorString(e);
+    const LaunchDims& d = c->dims;
+    char geo[256];
+    std::snprintf(geo, sizeof(geo), " [windows %d, grids %d/%d/%d/%d/%d, schur %d warps x %d sets x %d, chol %d (big %d), smem %zu/%zu/%zu/%zu]",
+                  d.n_windows, d.point_grid, d.imu_grid, d.gather_grid, d.reduce_grid, d.assemble_grid, d.sp_warps, d.sp_sets, d.sp_grid,
+                  d.chol_cluster, d.chol_big_tiles, d.smem_point, d.smem_lin, d.smem_chol, d.smem_sp);
+    c->err = std::string(what) + ": " + cudaGetErrorString(e) + geo;
     return true;
 }
 
@@ -607,6 +613,7 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
         // large reduced systems: blocked Cholesky over the whole GPU (chol_big.cu); small ones: one cluster per window
         ctx->dims.chol_big_tiles = (ctx->cap_n > ctx->chol_big_above) ? (ctx->cap_n + 63) / 64 : 0;
         if (const char* e = std::getenv("VILBA_CHOL_NB")) ctx->dims.chol_nb = (std::atoi(e) == 16) ? 16 : ctx->dims.chol_nb;
+        if (ctx->dims.chol_big_tiles > 0) ctx->dims.smem_chol = 0;  // the cluster kernel is not launched
         if (ctx->dims.smem_lin > 227 * 1024 || ctx->dims.smem_chol > 227 * 1024) {
             ctx->err = "window too large for the shared-memory stages";
             return VILBA_ERR_ARG;

@@ -24,3 +24,16 @@ def compare(r, o, w, chi_rtol=1e-6, state_atol=1e-5):
     assert np.abs(r.pt_xyz - o.pt_xyz).max(initial=0.0) <= state_atol
     assert np.array_equal(r.obs_outlier, o.obs_outlier)
     assert np.allclose(r.obs_chi2, o.obs_chi2, rtol=1e-6, atol=1e-9)
+
+
+def perturbed_window(name="tiny", window_index=0, scale=2.0, seed=5, **kw):
+    """A synthetic window whose initial estimates are far off (points +- scale m, free key-frame positions +- scale / 2):
+    Levenberg-Marquardt then REJECTS trials, which exercises the lambda growth, pop() and stale-error rules."""
+    from mc_slam_b200 import capi, synth
+    rng = np.random.default_rng(seed)
+    w = synth.make_config(name, window_index=window_index, **kw)
+    free = (w.kf_flags & capi.KF_FIXED) == 0
+    w.pt_xyz = (w.pt_xyz + rng.normal(0, scale, w.pt_xyz.shape)).astype(np.float32).astype(np.float64)
+    w.kf_state = w.kf_state.copy()
+    w.kf_state[free, 0:3] += rng.normal(0, scale * 0.5, (int(free.sum()), 3))
+    return w

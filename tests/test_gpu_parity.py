@@ -241,3 +241,31 @@ def test_lane_per_pair_schur_variant(oracle, monkeypatch):
             _compare(c.local_ba(w), oracle.local_ba(w), w)
     finally:
         c.close()
+
+
+def test_rejected_trials_on_the_device(ctx, oracle):
+    """Far-off initial estimates make LM reject trials: lambda growth, estimate restore and the stale per-edge chi2 that
+    the cull reads must all follow the oracle (and, through tests/test_oracle_vs_dense_lm.py, the dense numpy driver)."""
+    from parity_util import perturbed_window
+    for name, wi, scale, seed in (("tiny", 0, 2.0, 0), ("tiny", 0, 3.0, 6), ("small", 1, 2.0, 39), ("small", 1, 3.0, 39)):
+        w = perturbed_window(name, wi, scale, seed)
+        o = oracle.local_ba(w)
+        assert any(t["trials"] > 1 for t in o.trace)
+        _compare(ctx.local_ba(w), o, w, chi_rtol=1e-6, state_atol=1e-5)
+
+
+def test_contexts_of_different_window_sizes_do_not_disturb_each_other(vilba, oracle):
+    """The opt-in shared-memory limit of a kernel is process-wide, not per context: a context that only ever saw tiny
+    windows must not lower it under one that solves large windows (regression: 'eval: invalid argument')."""
+    big, small = vilba.Context(0), vilba.Context(0)
+    try:
+        wb = synth.make_window(n_kf=40, n_pts=500, mean_run=6.0, seed=synth.SEED_BASE + 78)
+        ws = synth.make_config("tiny", window_index=7)
+        ob, os_ = oracle.local_ba(wb), oracle.local_ba(ws)
+        _compare(big.local_ba(wb), ob, wb)
+        _compare(small.local_ba(ws), os_, ws)  # configures its kernels for a 4-key-frame window
+        _compare(big.local_ba(wb), ob, wb)
+        _compare(small.local_ba(ws), os_, ws)
+    finally:
+        big.close()
+        small.close()
