@@ -269,3 +269,86 @@ def test_contexts_of_different_window_sizes_do_not_disturb_each_other(vilba, ora
     finally:
         big.close()
         small.close()
+
+
+def _subset_obs(w, keep):
+    """Window with only the observations `keep` (boolean mask over the mono edges); points may end up with 0 or 1."""
+    import dataclasses
+    keep = np.asarray(keep, bool)
+    pt = np.repeat(np.arange(w.n_pts), np.diff(w.pt_obs_begin))
+    cnt = np.bincount(pt[keep], minlength=w.n_pts)
+    begin = np.zeros(w.n_pts + 1, np.int32)
+    np.cumsum(cnt, out=begin[1:])
+    return dataclasses.replace(w, pt_obs_begin=begin, obs_kf=w.obs_kf[keep].copy(), obs_uv=w.obs_uv[keep].copy(),
+                               obs_inv_sigma2=w.obs_inv_sigma2[keep].copy(), truth={})
+
+
+def test_irregular_observation_patterns(ctx, oracle):
+    """The generator only produces contiguous key-frame runs; real covisibility has gaps.  Random deletions give
+    arbitrary observer sets (the popcount edge lookup of the Schur kernel), points with one or no observation."""
+    rng = np.random.default_rng(11)
+    for name, wi, drop in (("small", 0, 0.35), ("c1", 1, 0.5), ("small", 3, 0.8)):
+        w = synth.make_config(name, window_index=wi)
+        w2 = _subset_obs(w, rng.uniform(size=w.n_obs) > drop)
+        m = np.diff(w2.pt_obs_begin)
+        assert (m == 0).any() or drop < 0.5
+        assert (m == 1).any()
+        _compare(ctx.local_ba(w2), oracle.local_ba(w2), w2)
+
+
+def test_vision_only_window_without_imu_edges(ctx, oracle):
+    """No EdgeNavStatePVR / EdgeNavStateBias at all: the velocity and bias blocks of H_pp are empty, only lambda keeps
+    the reduced system positive definite."""
+    import dataclasses
+    w = synth.make_config("small", window_index=2)
+    w0 = dataclasses.replace(w, imu_kf_i=np.zeros(0, np.int32), imu_kf_j=np.zeros(0, np.int32),
+                             imu_preint=np.zeros((0, 142)), truth={})
+    _compare(ctx.local_ba(w0), oracle.local_ba(w0), w0)
+
+
+def test_points_seen_only_by_fixed_keyframes_and_heavy_outliers(ctx, oracle):
+    w = synth.make_config("small", window_index=6, n_fixed_extra=3, outlier_frac=0.5)
+    fixed = (w.kf_flags & capi.KF_FIXED) != 0
+    pt = np.repeat(np.arange(w.n_pts), np.diff(w.pt_obs_begin))
+    only_fixed = np.zeros(w.n_obs, bool)
+    for p in range(0, w.n_pts, 7):  # every 7th point keeps only its observations from fixed key-frames (maybe none)
+        only_fixed |= (pt == p) & ~fixed[w.obs_kf]
+    w2 = _subset_obs(w, ~only_fixed)
+    _compare(ctx.local_ba(w2), oracle.local_ba(w2), w2)
+
+
+@pytest.mark.parametrize("n", [17, 40])
+def test_batches_that_split_over_lanes(ctx, oracle, n):
+    """16 or more windows are split over concurrent lanes (2 lanes at 17, 4 at 40), resident and end to end."""
+    wins = [synth.make_config("tiny" if i % 3 else "small", window_index=i % 5, outlier_frac=0.02 * (i % 4)) for i in range(n)]
+    refs = {}
+    ctx.upload_batch(wins)
+    assert ctx.batch_groups() == (2 if n == 17 else 4)
+    solved = ctx.solve_batch_resident()
+    down = ctx.download_batch()
+    e2e = ctx.local_ba_batch(wins)
+    for i, w in enumerate(wins):
+        key = (w.n_pts, i % 5, i % 4)
+        if key not in refs:
+            refs[key] = oracle.local_ba(w)
+        _compare(_merge(down[i], solved[i]), refs[key], w)
+        _compare(e2e[i], refs[key], w)
+
+
+def test_minimal_and_degenerate_windows(ctx, oracle):
+    # anchor + ONE free key-frame
+    w = synth.make_window(n_kf=2, n_pts=30, mean_run=2.0, seed=synth.SEED_BASE + 90)
+    assert w.n_free == 1
+    _compare(ctx.local_ba(w), oracle.local_ba(w), w)
+    # a free key-frame that observes nothing: only its IMU edges constrain it
+    w = synth.make_config("small", window_index=8)
+    blind = int(np.nonzero((w.kf_flags & capi.KF_FIXED) == 0)[0][2])
+    w2 = _subset_obs(w, w.obs_kf != blind)
+    _compare(ctx.local_ba(w2), oracle.local_ba(w2), w2)
+
+
+def test_many_keyframes_few_points(ctx, oracle):
+    """64 key-frames (gather Schur, reduced system n = 945 -> whole-GPU Cholesky) with a sparse map."""
+    w = synth.make_window(n_kf=64, n_pts=400, mean_run=5.0, seed=synth.SEED_BASE + 91)
+    assert 15 * w.n_free == 945
+    _compare(ctx.local_ba(w), oracle.local_ba(w), w)
