@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--keep-points", type=int, default=-1, help="keep only the first N map points (edge case: empty shards)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -45,6 +46,12 @@ def main():
     ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
     win = synth.make_config(args.config)
+    if args.keep_points >= 0:
+        import dataclasses
+        e1 = int(win.pt_obs_begin[args.keep_points])
+        win = dataclasses.replace(win, pt_xyz=win.pt_xyz[:args.keep_points].copy(), pt_obs_begin=win.pt_obs_begin[:args.keep_points + 1].copy(),
+                                  obs_kf=win.obs_kf[:e1].copy(), obs_uv=win.obs_uv[:e1].copy(),
+                                  obs_inv_sigma2=win.obs_inv_sigma2[:e1].copy(), truth={})
     sub, p0, p1, e0, e1 = sharding.shard_window(win, rank, world)
     res = None
     ms, iters = 0.0, 0

@@ -103,12 +103,13 @@ def test_batch_of_mixed_windows_in_one_launch(ctx, oracle):
 
 
 def test_batch_larger_than_one_chunk(ctx, oracle, monkeypatch):
-    """More windows than one batched launch holds: chunks are pipelined over two lanes."""
+    """More windows than the lanes hold at once: several rounds of concurrent lanes."""
     monkeypatch.setenv("VILBA_MAX_BATCH", "3")
     from mc_slam_b200 import api
     c = api.Context(0)
     try:
-        wins = [synth.make_config("tiny", window_index=i, outlier_frac=0.03 * i) for i in range(8)]
+        # max_batch 3 x 4 lanes = 12 windows per round: 14 windows take two rounds
+        wins = [synth.make_config("tiny", window_index=i % 7, outlier_frac=0.03 * (i % 7)) for i in range(14)]
         for w, r in zip(wins, c.local_ba_batch(wins)):
             _compare(r, oracle.local_ba(w), w)
     finally:

@@ -60,10 +60,10 @@ def test_merge_is_the_inverse_of_the_partition():
     assert m.trace[0]["n_active_edges"] == w.n_obs + 2 * w.n_imu
 
 
-def _run_worker(nproc, config, port):
+def _run_worker(nproc, config, port, extra=()):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_worker.py"),
-           "--config", config, "--check", "--steps", "1", "--warmup", "0"]
+           "--config", config, "--check", "--steps", "1", "--warmup", "0", *extra]
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "SHARDED" in p.stdout and '"parity": "ok"' in p.stdout and '"ranks_identical": true' in p.stdout, p.stdout[-2000:]
@@ -82,3 +82,12 @@ def test_sharded_solve_world_2():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run_worker(2, "c1", 29612)
+
+
+@pytest.mark.gpu
+def test_sharded_solve_with_an_empty_shard():
+    """One map point on two ranks: rank 1 owns no points and no IMU edges, its partial sums are zeros."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_worker(2, "tiny", 29613, ("--keep-points", "1"))
