@@ -856,6 +856,7 @@ int solve_batch(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_
 // pack the results of every window on the device, one D2H, scatter into the caller's arrays
 int download_batch(vilba_ctx* ctx, vilba_result* out) {
     if (ctx->n_win <= 0) return VILBA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");  // lanes run on their own host threads
     cudaStream_t s = ctx->stream;
     CK(launch_export(s, ctx->dwp, ctx->dims), "export");
     ctx->stats.kernel_launches += 1;

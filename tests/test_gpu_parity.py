@@ -353,3 +353,23 @@ def test_many_keyframes_few_points(ctx, oracle):
     w = synth.make_window(n_kf=64, n_pts=400, mean_run=5.0, seed=synth.SEED_BASE + 91)
     assert 15 * w.n_free == 945
     _compare(ctx.local_ba(w), oracle.local_ba(w), w)
+
+
+def test_context_on_the_second_device(vilba, oracle):
+    """Lanes run on their own host threads: every entry point has to select the context's device itself."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    c = vilba.Context(1)
+    try:
+        wins = [synth.make_config("tiny", window_index=i % 4) for i in range(20)]
+        refs = [oracle.local_ba(w) for w in wins[:4]]
+        c.upload_batch(wins)
+        solved, down = c.solve_batch_resident(), c.download_batch()
+        for i, w in enumerate(wins):
+            _compare(_merge(down[i], solved[i]), refs[i % 4], w)
+        for i, r in enumerate(c.local_ba_batch(wins)):
+            _compare(r, refs[i % 4], wins[i])
+        _compare(c.local_ba(wins[1]), refs[1], wins[1])
+    finally:
+        c.close()
