@@ -76,3 +76,60 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "vilba_oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_blob_and_shard_entry_points_from_plain_c(tmp_path, built):
+    """The host-only entry points called the way a C / C++ maintainer would: a C program linked against libvilba.so
+    serialises a window it builds itself, reads it back as a zero-copy view, and asks for the point shards."""
+    src = tmp_path / "blob.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "vilba.h"
+int main(void) {
+    enum { K = 3, NI = 2, P = 4, E = 7 };
+    double kf[K * VILBA_NS_DOUBLES] = {0}, pre[NI * VILBA_PREINT_DOUBLES] = {0}, pts[P * 3];
+    unsigned char flags[K] = {VILBA_KF_FIXED | VILBA_KF_HAS_BIAS, VILBA_KF_HAS_BIAS, VILBA_KF_HAS_BIAS};
+    int64_t ids[K] = {10, 11, 12};
+    int32_t ii[NI] = {0, 1}, jj[NI] = {1, 2}, begin[P + 1] = {0, 2, 4, 5, 7}, okf[E] = {0, 1, 1, 2, 0, 1, 2};
+    float uv[2 * E], is2[E];
+    for (int i = 0; i < K; ++i) kf[i * VILBA_NS_DOUBLES + 6] = 1.0;
+    for (int i = 0; i < P * 3; ++i) pts[i] = 0.5 * i;
+    for (int i = 0; i < E; ++i) { uv[2 * i] = 10.f * i; uv[2 * i + 1] = 3.f * i; is2[i] = 1.f; }
+    vilba_window w;
+    memset(&w, 0, sizeof(w));
+    w.n_kf = K; w.n_imu = NI; w.n_pts = P; w.n_obs = E;
+    w.kf_state = kf; w.kf_flags = flags; w.kf_id = ids; w.imu_kf_i = ii; w.imu_kf_j = jj; w.imu_preint = pre;
+    w.pt_xyz = pts; w.pt_obs_begin = begin; w.obs_kf = okf; w.obs_uv = uv; w.obs_inv_sigma2 = is2;
+    w.fx = 458.654; w.fy = 457.296; w.cx = 367.215; w.cy = 248.375;
+    w.Rbc[0] = w.Rbc[4] = w.Rbc[8] = 1.0; w.gravity[2] = -9.81;
+    size_t n = vilba_window_blob_size(&w), written = 0;
+    uint64_t* buf = (uint64_t*)calloc((n + 7) / 8, 8);
+    if (!n || vilba_window_serialize(&w, buf, n, &written) != VILBA_OK || written != n) return 1;
+    if (vilba_window_serialize(&w, buf, n - 1, &written) == VILBA_OK) return 2;   /* capacity too small */
+    vilba_window v;
+    if (vilba_window_deserialize(buf, n, &v) != VILBA_OK) return 3;
+    if (v.n_kf != K || v.n_obs != E || v.kf_id[2] != 12 || v.obs_kf[6] != 2 || v.pt_xyz[11] != 5.5 || v.obs_uv[13] != 18.f ||
+        v.fx != w.fx || v.gravity[2] != -9.81 || memcmp(v.pt_obs_begin, begin, sizeof(begin)) != 0) return 4;
+    ((unsigned char*)buf)[300] ^= 1;                                            /* corrupt the payload */
+    if (vilba_window_deserialize(buf, n, &v) == VILBA_OK) return 5;
+    ((unsigned char*)buf)[300] ^= 1;
+    if (vilba_window_deserialize((char*)buf + 4, n - 4, &v) == VILBA_OK) return 6;  /* misaligned / not a blob */
+    int32_t p0, p1, total = 0;
+    for (int r = 0; r < 3; ++r) {
+        if (vilba_shard_points(&w, r, 3, &p0, &p1) != VILBA_OK || p1 < p0) return 7;
+        total += p1 - p0;
+    }
+    if (total != P || vilba_shard_points(&w, 3, 3, &p0, &p1) == VILBA_OK) return 8;
+    printf("ok %zu %s\n", n, vilba_version());
+    free(buf);
+    return 0;
+}
+''')
+    exe = tmp_path / "blob"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libvilba.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)]).decode()
+    assert out.startswith("ok ") and "vilba" in out
