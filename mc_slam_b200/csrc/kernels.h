@@ -130,6 +130,8 @@ struct DevWindow {
     int* pair_eb_rw;
     unsigned long long* pt_mask;  // P * 8: 256-bit key-frame masks per map point (all observers | free observers)
     LmState* lm;
+    double* chi_partial;     // 2 * point_grid: per-CTA partial sums of chi2 and the landmark part of the gain scale
+    unsigned* chi_counter;   // CTAs of update_eval that have delivered their partial
     long long* dbg;  // optional debug counters (16 x int64), may be null
     int dbg_flags;   // timing-ablation switches (only honoured by -DVILBA_CHOL_TIMING builds)
     int chol_stage;  // 1 if the Cholesky launch carries the shared-memory row stage of the back substitution

@@ -133,8 +133,10 @@ __global__ void __launch_bounds__(kPointThreads, 2) update_eval_kernel(const Dev
             chi += rho0;
         }
     }
-    // CTA reduction, then one atomic per CTA
+    // CTA reduction, one partial per CTA; the last CTA to arrive adds the partials in a fixed order, so that chi2 and the
+    // gain scale -- and with them every LM decision -- are bit-reproducible from run to run (no floating-point atomics)
     __shared__ double red[2][kPointThreads / 32];
+    __shared__ bool is_last;
     chi = warp_sum(chi);
     scale = warp_sum(scale);
     if (lane == 0) {
@@ -145,8 +147,26 @@ __global__ void __launch_bounds__(kPointThreads, 2) update_eval_kernel(const Dev
     if (threadIdx.x == 0) {
         double c = 0.0, s = 0.0;
         for (int i = 0; i < warps_per_cta; ++i) c += red[0][i], s += red[1][i];
-        atomicAdd(&w.lm->chi_acc, c);
-        if (APPLY) atomicAdd(&w.lm->scale_acc, s);
+        w.chi_partial[2 * blockIdx.x] = c;
+        w.chi_partial[2 * blockIdx.x + 1] = s;
+        __threadfence();
+        is_last = atomicAdd(w.chi_counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        double c = 0.0, s = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) {
+            c += __ldcg(w.chi_partial + 2 * i);
+            s += __ldcg(w.chi_partial + 2 * i + 1);
+        }
+        c = warp_sum(c);
+        s = warp_sum(s);
+        if (lane == 0) {
+            w.lm->chi_acc = c;
+            if (APPLY) w.lm->scale_acc = s;
+            *w.chi_counter = 0u;
+        }
     }
 }
 
@@ -370,6 +390,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const DevWindow* __restrict_
     }
     int* lm = reinterpret_cast<int*>(w.lm);
     for (int i = tid; i < (int)(sizeof(LmState) / sizeof(int)); i += nt) lm[i] = 0;
+    if (tid == 0) *w.chi_counter = 0u;
 }
 
 __global__ void __launch_bounds__(256) export_kernel(const DevWindow* __restrict__ wp) {

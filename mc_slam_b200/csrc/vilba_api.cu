@@ -80,7 +80,7 @@ struct Layout {
     // work region; offsets relative to wk_base
     size_t edge_pt, pair_begin, pair_ea, pair_eb, pt_mask;
     size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y,
-        schur_partial, ts_rec, ts_hdr, S, Lfac, cminv, cdinv, bs, x, dbg, outlier, Hpp_part, S_part, hpp_span, s_span, wk_bytes;
+        schur_partial, ts_rec, ts_hdr, S, Lfac, cminv, cdinv, bs, x, dbg, outlier, chi_partial, chi_counter, Hpp_part, S_part, hpp_span, s_span, wk_bytes;
 };
 
 struct WinMeta {
@@ -155,6 +155,8 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bo
     L.x = take(sizeof(double) * n);
     L.dbg = take(sizeof(long long) * 16);
     L.outlier = take(E);
+    L.chi_partial = take(sizeof(double) * 2 * (size_t)lin_ctas);
+    L.chi_counter = take(sizeof(unsigned) * 4);
     L.Hpp_part = take(sharded ? L.hpp_span : 0);  // send buffers of the two allreduces
     L.S_part = take(sharded ? L.s_span : 0);
     L.wk_bytes = o;
@@ -474,6 +476,8 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.x = reinterpret_cast<double*>(wk + L.x);
     dw.lm = lm;
     dw.dbg = reinterpret_cast<long long*>(wk + L.dbg);
+    dw.chi_partial = reinterpret_cast<double*>(wk + L.chi_partial);
+    dw.chi_counter = reinterpret_cast<unsigned*>(wk + L.chi_counter);
     if (const char* e = std::getenv("VILBA_CHOL_ABLATE")) dw.dbg_flags = std::atoi(e);
     dw.fx = w->fx, dw.fy = w->fy, dw.cx = w->cx, dw.cy = w->cy;
     for (int r = 0; r < 3; ++r)
