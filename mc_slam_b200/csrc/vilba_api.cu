@@ -264,13 +264,19 @@ int check_window(const vilba_window* w) {
     }
     if (w->n_pts && (w->pt_obs_begin[0] != 0 || w->pt_obs_begin[w->n_pts] != w->n_obs)) return VILBA_ERR_ARG;
     if (!w->n_pts && w->n_obs) return VILBA_ERR_ARG;
-    for (int e = 0; e < w->n_obs; ++e)
-        if (w->obs_kf[e] < 0 || w->obs_kf[e] >= w->n_kf) return VILBA_ERR_ARG;
-    // observations of a point ordered by key-frame (MapPoint::GetObservations order), each key-frame once
+    // one pass over the observations: key-frame indices in range, and the observations of a point ordered by
+    // key-frame (MapPoint::GetObservations order), each key-frame once
+    const int32_t* kf = w->obs_kf;
+    const int K = w->n_kf;
     for (int p = 0; p < w->n_pts; ++p) {
-        if (w->pt_obs_begin[p + 1] < w->pt_obs_begin[p]) return VILBA_ERR_ARG;
-        for (int e = w->pt_obs_begin[p] + 1; e < w->pt_obs_begin[p + 1]; ++e)
-            if (w->obs_kf[e] <= w->obs_kf[e - 1]) return VILBA_ERR_ARG;
+        const int e0 = w->pt_obs_begin[p], e1 = w->pt_obs_begin[p + 1];
+        if (e1 < e0 || e0 < 0 || e1 > w->n_obs) return VILBA_ERR_ARG;
+        int prev = -1;
+        for (int e = e0; e < e1; ++e) {
+            const int k = kf[e];
+            if (k <= prev || k >= K) return VILBA_ERR_ARG;  // also rejects k < 0
+            prev = k;
+        }
     }
     return VILBA_OK;
 }
