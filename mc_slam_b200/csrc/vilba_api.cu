@@ -218,7 +218,7 @@ struct vilba_ctx {
     std::vector<int> split_first;        // first window of every lane (+ end)
     cudaEvent_t start_after = nullptr;   // lane: event of the parent stream the solve starts after
     cudaEvent_t ev_done = nullptr;       // lane: recorded behind the last kernel of a solve
-    std::vector<vilba_ctx*> lanes;  // sub-contexts of vilba_local_ba_batch: chunks of the batch are pipelined over them
+    std::vector<vilba_ctx*> lanes;  // sub-contexts the windows of a large batch are split over
     int n_lanes = 4;                // env VILBA_BATCH_LANES
     std::vector<cudaEvent_t> probes;  // 8 events per profiled slot
     size_t probes_used = 0;
@@ -1217,10 +1217,9 @@ int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, c
     return r;
 }
 
-// Independent windows (BASELINE config 5).  The windows are cut into chunks of up to kMaxBatch; every chunk is
-// ONE batched solve (each kernel launched once for all its windows), and the chunks are pipelined over a few
-// sub-contexts ("lanes", one host thread each) so that the flatten / H2D / D2H of one chunk overlaps the
-// solve of another.
+// Independent windows (BASELINE config 5).  16 or more windows are split over up to 4 lanes (sub-contexts with their
+// own streams, arena and host thread) that upload, solve and download concurrently; every lane is ONE batched solve
+// (each kernel launched once for all its windows).  More than max_batch * lanes windows take several rounds.
 int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* win, vilba_result* out) {
     if (!ctx || n_windows < 0 || (n_windows && (!win || !out))) return VILBA_ERR_ARG;
     if (n_windows == 0) return VILBA_OK;
