@@ -1,0 +1,33 @@
+/*
+ * vilba_diag.h -- diagnostic entry points of libvilba.so.  NOT part of the reference boundary (include/vilba.h):
+ * they exist so that single kernels of the path can be checked against numpy / timed in isolation by tests/ and
+ * tools/ without building a whole window around them.
+ */
+#ifndef VILBA_DIAG_H
+#define VILBA_DIAG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Solve n_windows copies of one dense symmetric system S x = b (S: n x n, full symmetric storage) with a
+ * reduced-system kernel of the library (the kernels that replace LinearSolverEigen::solve,
+ * g2o/solvers/linear_solver_eigen.h:94-124):
+ *   variant 0: cluster kernel, trailing matrix in L2           (chol.cu)
+ *   variant 1: look-ahead cluster kernel, trailing matrix in shared memory (chol_la.cu)
+ *   variant 2: whole-GPU blocked factorisation                 (chol_big.cu)
+ * `cluster` = CTAs per system (variants 0, 1).  The kernel is launched `reps` times (system restored in
+ * between); avg_us receives the mean device time of one launch (CUDA events around the launch only).
+ * x_out: n (solution of window 0), fail_out: the kernel's failure flag.  Returns a VILBA_* status. */
+int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S, const double* b, int32_t variant, int32_t cluster,
+                           int32_t n_windows, int32_t reps, double* x_out, int32_t* fail_out, double* avg_us);
+
+/* 1 if variant / cluster can handle a system of dimension n (shared-memory capacity), else 0 */
+int vilba_diag_dense_supported(int32_t n, int32_t variant, int32_t cluster);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILBA_DIAG_H */

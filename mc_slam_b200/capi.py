@@ -360,6 +360,10 @@ EXPORTED_SYMBOLS = [  # every symbol include/vilba.h declares
     "vilba_reset_stats",
     "vilba_set_profiling",
 ]
+DIAG_SYMBOLS = [  # every symbol include/vilba_diag.h declares (diagnostics, not the reference boundary)
+    "vilba_diag_dense_solve",
+    "vilba_diag_dense_supported",
+]
 
 _lib = None
 
@@ -434,6 +438,33 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vilba_reset_stats.restype = None
     lib.vilba_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.vilba_set_profiling.restype = None
+    lib.vilba_diag_dense_solve.argtypes = [
+        C.c_int32, C.c_int32, _c_double_p, _c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _c_double_p,
+        _c_int32_p, _c_double_p,
+    ]
+    lib.vilba_diag_dense_solve.restype = C.c_int
+    lib.vilba_diag_dense_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.vilba_diag_dense_supported.restype = C.c_int
     if path is None:
         _lib = lib
     return lib
+
+
+def diag_dense_solve(S, b, variant=1, cluster=8, n_windows=1, reps=1, device=0):
+    """Solve S x = b with one of the library's reduced-system kernels (include/vilba_diag.h).
+    Returns (x, fail_flag, average microseconds per launch)."""
+    import numpy as np
+
+    lib = load_library()
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    n = S.shape[0]
+    x = np.zeros(n)
+    fail = C.c_int32(0)
+    us = C.c_double(0.0)
+    st = lib.vilba_diag_dense_solve(
+        device, n, S.ctypes.data_as(_c_double_p), b.ctypes.data_as(_c_double_p), variant, cluster, n_windows, reps,
+        x.ctypes.data_as(_c_double_p), C.byref(fail), C.byref(us))
+    if st != 0:
+        raise RuntimeError(f"vilba_diag_dense_solve(n={n}, variant={variant}, cluster={cluster}) returned {st}")
+    return x, int(fail.value), float(us.value)

@@ -191,6 +191,8 @@ struct LaunchDims {
     int sp_tile_pts;      // map points per shared-memory tile
     int sp_pair_lanes;    // 1: one lane per block pair (36 accumulators), one CTA covers all pairs of the window
     int chol_cluster;     // CTAs of the Cholesky cluster
+    int chol_la;          // 1: look-ahead cluster kernel with the trailing matrix in shared memory (chol_la.cu)
+    int chol_n;           // largest reduced system of the batch (sizes the shared memory of chol_la)
     int chol_big_tiles;   // > 0: whole-GPU blocked Cholesky (chol_big.cu) with this many 64-column steps, instead of the cluster kernel
     int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
     size_t smem_point;    // dynamic shared memory of update_eval / flags
@@ -211,6 +213,13 @@ size_t schur_partial_doubles(int n_free);
 bool chol_has_stage(int n_cap);
 int chol_block_size(int n_cap);
 cudaError_t configure_chol_big(int n_cap);
+// look-ahead cluster kernel with the trailing matrix in shared memory (chol_la.cu)
+int chol_la_tiles_per_thread(int n, int cluster);
+size_t chol_la_smem_bytes(int n, int cluster);
+size_t chol_la_scratch_doubles(int n);   // DevWindow::cminv must hold this many doubles
+bool chol_la_fits(int n, int cluster);
+cudaError_t configure_chol_la();
+cudaError_t launch_chol_la(cudaStream_t s, const DevWindow* wp, int n_windows, int cluster, int n_cap);
 cudaError_t launch_chol_big(cudaStream_t s, cudaStream_t side, cudaEvent_t ev_trsm, cudaEvent_t ev_rest, const DevWindow* wp,
                             const LaunchDims& d);
 cudaError_t configure_kernels(const LaunchDims& d);  // cudaFuncSetAttribute for the large-smem kernels

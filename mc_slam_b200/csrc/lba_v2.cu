@@ -1006,15 +1006,14 @@ cudaError_t configure_chol(const LaunchDims& d);
 cudaError_t configure_kernels(const LaunchDims& d) {
     cudaError_t e = opt_in_max_smem(linearize_v2_kernel);
     if (e != cudaSuccess) return e;
-    if (d.smem_sp > 0) {
-        e = opt_in_max_smem(schur_tile_kernel);
-        if (e != cudaSuccess) return e;
-        e = opt_in_max_smem(schur_tile_pair_kernel);
-        if (e != cudaSuccess) return e;
-    }
+    e = opt_in_max_smem(schur_tile_kernel);
+    if (e != cudaSuccess) return e;
+    e = opt_in_max_smem(schur_tile_pair_kernel);
+    if (e != cudaSuccess) return e;
     e = configure_point_kernels(d);
     if (e != cudaSuccess) return e;
-    if (d.chol_big_tiles > 0 && (e = configure_chol_big(d.chol_big_tiles * 64)) != cudaSuccess) return e;
+    if ((e = configure_chol_big(0)) != cudaSuccess) return e;
+    if ((e = configure_chol_la()) != cudaSuccess) return e;
     return configure_chol(d);
 }
 
@@ -1058,7 +1057,10 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     }
     if (comm && (e = comm->reduce(comm->self, RED_S, s)) != cudaSuccess) return e;  // S | b_s = sum of the partial reduced systems
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
-    if ((e = (d.chol_big_tiles > 0 ? launch_chol_big(s, side, fork, join, wp, d) : launch_chol_cluster(s, wp, d))) != cudaSuccess) return e;
+    if (d.chol_big_tiles > 0) e = launch_chol_big(s, side, fork, join, wp, d);
+    else if (d.chol_la) e = launch_chol_la(s, wp, d.n_windows, d.chol_cluster, d.chol_n);
+    else e = launch_chol_cluster(s, wp, d);
+    if (e != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;
     if ((e = launch_update_eval_apply(s, wp, d)) != cudaSuccess) return e;
     if (comm && (e = comm->reduce(comm->self, RED_CHI, s)) != cudaSuccess) return e;  // chi2 and the landmark part of the gain scale

@@ -150,7 +150,7 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bo
     L.bs = take(sizeof(double) * n);  // directly behind S: one allreduce covers S | b_s of a sharded window
     L.s_span = L.bs + sizeof(double) * n - L.S;
     L.Lfac = take(sizeof(double) * lds * n);
-    L.cminv = take(sizeof(double) * 256 * (n / 16 + 2));
+    L.cminv = take(sizeof(double) * std::max<size_t>(256 * (n / 16 + 2), chol_la_scratch_doubles((int)n)));
     L.cdinv = take(sizeof(double) * n);
     L.x = take(sizeof(double) * n);
     L.dbg = take(sizeof(long long) * 16);
@@ -189,6 +189,7 @@ struct vilba_ctx {
     size_t in_total = 0, out_total = 0, lm_base = 0, out_region = 0;  // arena: [in | out | lm array | work]
     LaunchDims dims;
     int chol_cluster = 8;
+    int chol_la_mode = 1;            // env VILBA_CHOL_LA: 0 never, 1 automatic, 2 always (when the tiles fit)
     int chol_big_above = 480;        // env VILBA_CHOL_BIG_ABOVE: reduced systems larger than this use chol_big.cu (the cluster
                                      // kernel's panel + row stage fit in shared memory up to n = 508)
     bool schur_gather_only = false;  // env VILBA_SCHUR=gather (ablation)
@@ -332,7 +333,9 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
     // tile-scan Schur kernel for windows of <= 32 key-frames, else the gather over pair lists
     d.sp_warps = d.sp_sets = d.sp_grid = d.sp_tile_pts = 0;
     d.smem_sp = 0;
-    if (!ctx->schur_gather_only && max_K > 0 && schur_tile_fits(ctx->cap_K, ctx->cap_nf)) {
+    // (the Schur and Cholesky variants follow the CURRENT batch, not the capacities: one large window must not push
+    // every later small one onto the paths for large windows)
+    if (!ctx->schur_gather_only && max_K > 0 && schur_tile_fits(max_K, max_nf)) {
         const int max_pairs = max_nf * (max_nf + 1) / 2;
         d.sp_sets = ctx->sp_sets > 0 ? ctx->sp_sets : (max_pairs >= 40 ? 4 : 1);
         const int max_groups = (max_pairs + 1) / 2;  // a lane group owns two block pairs (a close and a distant one)
@@ -351,12 +354,32 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
         if (const char* e = std::getenv("VILBA_SP_TILE")) d.sp_tile_pts = std::max(2, std::min(d.sp_tile_pts, std::atoi(e)));
         d.smem_sp = schur_tile_smem_bytes(max_K, d.sp_tile_pts);
     }
-    // Cholesky: as many CTAs per window as the machine has to spare (one 8-CTA cluster for a single window,
-    // smaller clusters when many windows share the SMs: a CTA is more efficient the fewer partners it waits for)
+    // Cholesky.  Large reduced systems: blocked factorisation over the whole GPU (chol_big.cu); small ones: one cluster
+    // per window, as many CTAs as the machine has to spare (one 8-CTA cluster for a single window, smaller clusters when
+    // many windows share the SMs: a CTA is more efficient the fewer partners it waits for)
+    const int n_cur = 15 * max_nf;
+    d.chol_big_tiles = (n_cur > ctx->chol_big_above) ? (n_cur + 63) / 64 : 0;
+    d.chol_nb = chol_block_size(n_cur);
+    if (const char* e = std::getenv("VILBA_CHOL_NB")) d.chol_nb = (std::atoi(e) == 16) ? 16 : d.chol_nb;
+    d.smem_chol = d.chol_big_tiles > 0 ? 0 : chol_smem_bytes(n_cur);
     int cl = 1;
     const int n_all = std::max(n_win, ctx->batch_total_hint);  // windows of all concurrent lanes share the SMs
     while (2 * cl <= ctx->chol_cluster && 2 * cl * n_all <= sm) cl *= 2;
     d.chol_cluster = n_win == 1 ? ctx->chol_cluster : cl;
+    // the look-ahead kernel (chol_la.cu) keeps the trailing matrix in the shared memory of the cluster: it needs enough
+    // CTAs per window for the tiles to fit (n = 285: 4, n = 135: 1).  One window: the full cluster (latency).  A batch:
+    // the smallest cluster that fits, as long as all windows of all lanes still find room on the machine
+    d.chol_la = 0;
+    d.chol_n = 15 * max_nf;
+    if (ctx->chol_la_mode != 0 && d.chol_big_tiles == 0 && max_nf > 0) {
+        int c = n_win == 1 ? ctx->chol_cluster : 1;
+        while (c <= 8 && !chol_la_fits(d.chol_n, c)) c *= 2;
+        const bool room = n_win == 1 || ctx->chol_la_mode == 2 || c * n_all <= 2 * sm;
+        if (c <= std::max(8, ctx->chol_cluster) && chol_la_fits(d.chol_n, c) && room) {
+            d.chol_la = 1;
+            d.chol_cluster = c;
+        }
+    }
     return d;
 }
 
@@ -618,18 +641,11 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
         ctx->cap_n = std::max(ctx->cap_n, 15 * ctx->cap_nf);
         ctx->dims.smem_point = point_smem_bytes(ctx->cap_K);
         ctx->dims.smem_lin = linearize_smem_bytes(ctx->cap_K, ctx->cap_nf);
-        ctx->dims.smem_chol = chol_smem_bytes(ctx->cap_n);
-        ctx->dims.chol_nb = chol_block_size(ctx->cap_n);
-        // large reduced systems: blocked Cholesky over the whole GPU (chol_big.cu); small ones: one cluster per window
-        ctx->dims.chol_big_tiles = (ctx->cap_n > ctx->chol_big_above) ? (ctx->cap_n + 63) / 64 : 0;
-        if (const char* e = std::getenv("VILBA_CHOL_NB")) ctx->dims.chol_nb = (std::atoi(e) == 16) ? 16 : ctx->dims.chol_nb;
-        if (ctx->dims.chol_big_tiles > 0) ctx->dims.smem_chol = 0;  // the cluster kernel is not launched
-        if (ctx->dims.smem_lin > 227 * 1024 || ctx->dims.smem_chol > 227 * 1024) {
+        if (ctx->dims.smem_lin > 227 * 1024) {
             ctx->err = "window too large for the shared-memory stages";
             return VILBA_ERR_ARG;
         }
         ctx->dims.chol_cluster = ctx->chol_cluster;
-        ctx->dims.smem_sp = schur_tile_fits(ctx->cap_K, ctx->cap_nf) ? 110 * 1024 : 0;  // upper bound of any tile geometry
         CK(configure_kernels(ctx->dims), "cudaFuncSetAttribute");
         drop_graphs(ctx);
     }
@@ -665,7 +681,7 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     LmState* lm0 = reinterpret_cast<LmState*>(d + ctx->lm_base);
     for (int i = 0; i < n_win; ++i) {
         fill_dev_window(ctx, &wins[i], meta[i], d, lm0 + i, ctx->dw[i]);
-        ctx->dw[i].chol_stage = chol_has_stage(ctx->cap_n) ? 1 : 0;
+        ctx->dw[i].chol_stage = chol_has_stage(15 * max_nf) ? 1 : 0;
     }
     std::memcpy(ctx->pinned_small.base, ctx->dw.data(), sizeof(DevWindow) * (size_t)n_win);
     CK(cudaMemcpyAsync(ctx->dwp, ctx->pinned_small.base, sizeof(DevWindow) * (size_t)n_win, cudaMemcpyHostToDevice,
@@ -712,7 +728,7 @@ bool same_dims(const LaunchDims& a, const LaunchDims& b) {
            a.gather_grid == b.gather_grid && a.reduce_grid == b.reduce_grid && a.assemble_grid == b.assemble_grid &&
            a.sp_warps == b.sp_warps && a.sp_sets == b.sp_sets && a.sp_grid == b.sp_grid && a.sp_tile_pts == b.sp_tile_pts &&
            a.sp_pair_lanes == b.sp_pair_lanes && a.chol_cluster == b.chol_cluster && a.chol_big_tiles == b.chol_big_tiles &&
-           a.chol_nb == b.chol_nb && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.smem_chol == b.smem_chol &&
+           a.chol_nb == b.chol_nb && a.chol_la == b.chol_la && a.chol_n == b.chol_n && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.smem_chol == b.smem_chol &&
            a.smem_sp == b.smem_sp;
 }
 
@@ -1041,6 +1057,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("VILBA_CHOL_BIG_ABOVE")) ctx->chol_big_above = std::atoi(e);
+    if (const char* e = std::getenv("VILBA_CHOL_LA")) ctx->chol_la_mode = std::atoi(e);
     if (const char* e = std::getenv("VILBA_SCHUR")) ctx->schur_gather_only = std::strcmp(e, "gather") == 0;
     if (const char* e = std::getenv("VILBA_SP_GRID")) ctx->sp_grid_cap = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_SP_SETS")) ctx->sp_sets = std::max(1, std::atoi(e));

@@ -24,12 +24,14 @@ def built():
 
 
 def test_header_symbols_are_exported(built):
-    hdr = open(os.path.join(ROOT, "include", "vilba.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # declarations only, not prose in comments
-    declared = set(re.findall(r"\b(vilba_[a-z_]+)\s*\(", hdr))
-    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
-    for sym in declared:
-        assert getattr(built, sym) is not None
+    for header, table in (("vilba.h", capi.EXPORTED_SYMBOLS), ("vilba_diag.h", capi.DIAG_SYMBOLS)):
+        hdr = open(os.path.join(ROOT, "include", header)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # declarations only, not prose in comments
+        declared = set(re.findall(r"\b(vilba_[a-z_]+)\s*\(", hdr))
+        assert declared == set(table), declared ^ set(table)
+        for sym in declared:
+            assert getattr(built, sym) is not None
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["vilba.h", "vilba_diag.h"]
 
 
 def test_struct_layout_matches_c(tmp_path):
