@@ -177,7 +177,7 @@ struct vilba_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr;
     vilba_params prm;
     Arena arena, preint_arena;
-    Pinned pinned, pinned_out, pinned_small;
+    Pinned pinned, pinned_out, pinned_small, pinned_preint;  // (pre-integration has its own staging: an upload's H2D may still read `pinned`)
     std::string err;
     int sm_count = 148;
     int max_batch = kMaxBatch;
@@ -593,6 +593,9 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
         return VILBA_ERR_ARG;
     }
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    // a captured sharded slot also holds the allreduces of slot_reduce(): their addresses and counts follow this window's
+    // layout (P, E, n_free, arena base), not only the launch geometry the graph cache is keyed on -- re-capture per window
+    if (ctx->comm) drop_graphs(ctx);
     std::vector<WinMeta>& meta = ctx->meta;
     meta.assign(n_win, WinMeta());
     std::vector<int> status(n_win, VILBA_OK);
@@ -779,7 +782,10 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
     for (int i = 0; i < ctx->n_win; ++i) first_trace[i] = lm[i].n_trace;
     // one trial per iteration when every step is accepted, plus spares for rejected trials
     int slots = iterations + (ctx->n_win > 1 ? 3 : 1);
-    for (int round = 0; round < 64; ++round) {
+    // every slot runs at least one trial of every unfinished window, so (iterations + 1) * max_trials slots always suffice
+    const int max_rounds = 2 + ((iterations + 1) * std::max(1, ctx->prm.max_trials)) / 2;
+    bool done = false;
+    for (int round = 0; round < max_rounds && !done; ++round) {
         for (int i = 0; i < slots; ++i) {
             if (graph)
                 CK(cudaGraphLaunch(exec, s), "graph launch");
@@ -789,10 +795,13 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
         }
         int r = read_lm(ctx, lm, stop_flag);
         if (r != VILBA_OK) return r;
-        bool done = true;
+        done = true;
         for (int i = 0; i < ctx->n_win; ++i) done = done && lm[i].phase == PH_DONE;
-        if (done) break;
         slots = 2;  // rejected trials used up the slack: keep going
+    }
+    if (!done) {
+        ctx->err = "LM stage did not finish within iterations * max_trials slots";
+        return VILBA_ERR_CUDA;
     }
     for (int wdx = 0; wdx < ctx->n_win; ++wdx) {
         vilba_result& o = out[wdx];
@@ -1098,6 +1107,7 @@ void vilba_destroy(vilba_ctx* ctx) {
     ctx->pinned.release();
     ctx->pinned_out.release();
     ctx->pinned_small.release();
+    ctx->pinned_preint.release();
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -1307,9 +1317,9 @@ int vilba_preintegrate_batch(vilba_ctx* ctx, int32_t n_pairs, const int32_t* sam
     const size_t in_end = o;
     const size_t o_out = take(sizeof(double) * 142 * (size_t)n_pairs);
     CK(ctx->preint_arena.reserve(o), "cudaMalloc(preint)");
-    CK(ctx->pinned.reserve(in_end > sizeof(double) * 142 * (size_t)n_pairs ? in_end : sizeof(double) * 142 * (size_t)n_pairs),
+    CK(ctx->pinned_preint.reserve(in_end > sizeof(double) * 142 * (size_t)n_pairs ? in_end : sizeof(double) * 142 * (size_t)n_pairs),
        "cudaMallocHost(preint)");
-    char* h = ctx->pinned.base;
+    char* h = ctx->pinned_preint.base;
     std::memcpy(h + o_sb, sample_begin, sizeof(int) * ((size_t)n_pairs + 1));
     std::memcpy(h + o_g, gyro, sizeof(double) * 3 * ns);
     std::memcpy(h + o_a, acc, sizeof(double) * 3 * ns);

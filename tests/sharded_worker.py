@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--keep-points", type=int, default=-1, help="keep only the first N map points (edge case: empty shards)")
+    ap.add_argument("--then", default="", help="afterwards solve this other config on the SAME context (different P, E, n_free) and check it")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -89,6 +90,23 @@ def main():
             _compare(merged, o, win)
             line["parity"] = "ok"
         print("SHARDED " + json.dumps(line), flush=True)
+    if args.then:  # a second window of another shape on the same communicator context (the normal SLAM use)
+        win2 = synth.make_config(args.then)
+        sub2, q0, q1, f0, f1 = sharding.shard_window(win2, rank, world)
+        if world > 1:
+            dist.barrier()
+        res2 = ctx.local_ba(sub2)
+        parts2 = [None] * world
+        if world > 1:
+            dist.all_gather_object(parts2, (res2, q0, q1, f0, f1))
+        else:
+            parts2 = [(res2, q0, q1, f0, f1)]
+        if rank == 0:
+            from oracle import pyoracle
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from parity_util import compare as _compare
+            _compare(sharding.merge_sharded(win2, parts2), pyoracle.local_ba(win2), win2)
+            print("SHARDED_THEN " + json.dumps({"config": args.then, "parity": "ok"}), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

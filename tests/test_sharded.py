@@ -77,6 +77,18 @@ def test_sharded_solve_world_1(config):
 
 
 @pytest.mark.gpu
+def test_sharded_context_solves_windows_of_different_shapes():
+    """Two windows with different P, E and n_free on ONE communicator context: the captured slot holds the allreduces'
+    addresses and counts, so it has to follow the window (a stale graph would reduce the wrong bytes)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr", "127.0.0.1",
+           "--master-port", "29614", os.path.join(ROOT, "tests", "sharded_worker.py"), "--config", "c1", "--check",
+           "--steps", "1", "--warmup", "0", "--then", "small"]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "SHARDED_THEN" in p.stdout and p.stdout.count('"parity": "ok"') == 2, p.stdout[-2000:]
+
+
+@pytest.mark.gpu
 def test_sharded_solve_world_2():
     import torch
     if torch.cuda.device_count() < 2:
