@@ -1,0 +1,105 @@
+"""ctypes binding of oracle/_ref/libref_imu.so: the reference's OWN so3 / IMUPreintegrator / NavState / imudata sources
+compiled unmodified against oracle/eigen_stub (oracle/Makefile target `ref`).  TEST INFRASTRUCTURE: the pin of the
+oracle's restatement; only tests/ and the golden-vector generators use it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libref_imu.so")
+REFERENCE = os.environ.get("VILBA_REFERENCE", "/root/reference")
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def available() -> bool:
+    """True if the compiled reference is there, or can be built here (the reference tree exists in this container only)."""
+    return os.path.exists(LIB_PATH) or os.path.isdir(os.path.join(REFERENCE, "src", "IMU"))
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REFERENCE}"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        l = C.CDLL(LIB_PATH)
+        l.ref_preintegrate.argtypes = [C.c_int32] + [_dp] * 6
+        l.ref_preintegrate.restype = None
+        for name, n in [("ref_so3_exp", 2), ("ref_so3_log", 2), ("ref_so3_mul", 3), ("ref_so3_inverse", 2), ("ref_so3_matrix", 2),
+                        ("ref_so3_from_matrix", 2), ("ref_so3_rotate", 3), ("ref_jacobian_r", 2), ("ref_jacobian_r_inv", 2),
+                        ("ref_so3_jacobian_r", 2), ("ref_so3_jacobian_r_inv", 2), ("ref_navstate_inc_pvr", 2),
+                        ("ref_navstate_inc_bias", 2), ("ref_imu_constants", 1)]:
+            f = getattr(l, name)
+            f.argtypes = [_dp] * n
+            f.restype = None
+        l.ref_build_info.restype = C.c_char_p
+        _lib = l
+    return _lib
+
+
+def _a(x, n=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+    assert n is None or a.size == n
+    return a
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _call(name, out_n, *ins):
+    out = np.zeros(out_n)
+    getattr(lib(), name)(*[_d(_a(i)) for i in ins], _d(out))
+    return out
+
+
+def preintegrate_batch(sample_begin, gyro, acc, dt, bg, ba) -> np.ndarray:
+    """IMUPreintegrator::reset + update per sample for every key-frame pair, like KeyFrame::ComputePreInt."""
+    sb = np.asarray(sample_begin, dtype=np.int64)
+    g, a, t = _a(gyro).reshape(-1, 3), _a(acc).reshape(-1, 3), _a(dt)
+    b1, b2 = _a(bg).reshape(-1, 3), _a(ba).reshape(-1, 3)
+    out = np.zeros((sb.size - 1, 142))
+    for p in range(sb.size - 1):
+        s0, s1 = int(sb[p]), int(sb[p + 1])
+        gi, ai, ti = np.ascontiguousarray(g[s0:s1]), np.ascontiguousarray(a[s0:s1]), np.ascontiguousarray(t[s0:s1])
+        lib().ref_preintegrate(s1 - s0, _d(gi), _d(ai), _d(ti), _d(np.ascontiguousarray(b1[p])), _d(np.ascontiguousarray(b2[p])),
+                               _d(out[p]))
+    return out
+
+
+def so3_exp(w): return _call("ref_so3_exp", 4, w)
+def so3_log(q): return _call("ref_so3_log", 3, q)
+def so3_mul(a, b): return _call("ref_so3_mul", 4, a, b)
+def so3_inverse(a): return _call("ref_so3_inverse", 4, a)
+def so3_matrix(a): return _call("ref_so3_matrix", 9, a).reshape(3, 3)
+def so3_from_matrix(R): return _call("ref_so3_from_matrix", 4, R)
+def so3_rotate(a, v): return _call("ref_so3_rotate", 3, a, v)
+def jacobian_r(w): return _call("ref_jacobian_r", 9, w).reshape(3, 3)
+def jacobian_r_inv(w): return _call("ref_jacobian_r_inv", 9, w).reshape(3, 3)
+def so3_jacobian_r(w): return _call("ref_so3_jacobian_r", 9, w).reshape(3, 3)
+def so3_jacobian_r_inv(w): return _call("ref_so3_jacobian_r_inv", 9, w).reshape(3, 3)
+
+
+def inc_pvr(ns, d):
+    s = _a(ns, 22).copy()
+    lib().ref_navstate_inc_pvr(_d(s), _d(_a(d, 9)))
+    return s
+
+
+def inc_bias(ns, d):
+    s = _a(ns, 22).copy()
+    lib().ref_navstate_inc_bias(_d(s), _d(_a(d, 6)))
+    return s
+
+
+def imu_constants(): return _call("ref_imu_constants", 4)
+def build_info() -> str: return lib().ref_build_info().decode()

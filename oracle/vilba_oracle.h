@@ -3,8 +3,12 @@
  * C entry points of the CPU oracle: a dependency-free restatement of the reference's g2o path
  * for Optimizer::LocalBundleAdjustmentNavState and IMUPreintegrator::update.  It is the checker
  * for tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never
- * the product.  PARITY UNPINNED: the reference ships no tests/golden vectors for this path and
- * cannot be compiled here (Eigen/OpenCV/CHOLMOD absent); see DESIGN.md.
+ * the product.  PARITY PARTLY PINNED: the reference ships no tests / golden vectors for this path.
+ * SO3, IMUPreintegrator, NavState and the IMU constants are pinned against the reference's OWN sources,
+ * compiled unmodified against a minimal Eigen stand-in (oracle/Makefile target `ref`, oracle/_ref/,
+ * tests/test_oracle_vs_ref.py, tests/golden/ref_imu_v1.npz).  The g2o machinery, src/IMU/g2otypes.cpp
+ * and src/Optimizer.cpp cannot be compiled here (all of g2o + Eigen + OpenCV + CHOLMOD) and stay
+ * RESTATED AND UNPINNED against executed reference code; see DESIGN.md section 2.
  */
 #ifndef VILBA_ORACLE_H
 #define VILBA_ORACLE_H
