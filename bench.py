@@ -15,7 +15,13 @@ value   : LM outer iterations / s over all windows, windows resident in HBM when
           (device time from CUDA events on the library's stream, L2 flushed between steps, max over ranks)
 e2e     : same metric through the C-ABI call vilba_local_ba_batch() with HOST buffers
           (flatten + H2D + solve + D2H inside the timed region)
-single_window : the same two numbers for ONE 20-KF window (latency-bound; BASELINE config 3)
+roofline / roofline_all : the dominant kernel group of the TIMED configuration / all four groups (per-group device
+          times from a pass with CUDA events between the kernels, lanes concurrent as in the timed pass)
+single_window : the same two numbers for ONE 20-KF window (latency-bound; BASELINE config 3) and their ratio to ONE
+          host thread of the CPU restatement (the north star's >= 50x target is written on this pair)
+c1, c2_preint, c4 : BASELINE configs 1, 2 and 4 on one GPU (N = 1 only)
+sharded_c4 : config 4 point-sharded over the N ranks (vilba_comm_init: NCCL allreduce of the partial normal equations
+          per LM trial, reduced system solved redundantly) -- the strong-scaling curve of the driver's 1/2/4/8 run
 Multi-GPU: windows are independent -> each rank owns its own batch, no data-path collective, "weak"
           scaling; torch.distributed only carries the barrier/max.
 """
@@ -114,6 +120,32 @@ def algorithmic_bytes_linearize(w):
     return w.n_obs * 20 + w.n_pts * 24 + e_free * 144 + w.n_pts * 96 + n * n * 4 + n * 8
 
 
+def _edges_to_free(w):
+    from mc_slam_b200 import capi
+    free = (w.kf_flags & capi.KF_FIXED) == 0
+    return int(np.count_nonzero(free[w.obs_kf]))
+
+
+def algorithmic_bytes_schur(w):
+    """B_schur = E'*144 + P*96 read + n^2*4 + n*8 written."""
+    n = 15 * w.n_free
+    return _edges_to_free(w) * 144 + w.n_pts * 96 + n * n * 4 + n * 8
+
+
+def algorithmic_bytes_update(w):
+    """B_bs + B_ev = (E'*144 + P*96 + n*8 + P*24) + (E*20 + P*48 + E*8)."""
+    n = 15 * w.n_free
+    return (_edges_to_free(w) * 144 + w.n_pts * 96 + n * 8 + w.n_pts * 24) + (w.n_obs * 20 + w.n_pts * 48 + w.n_obs * 8)
+
+
+def solve_flops(w):
+    n = 15 * w.n_free
+    return n ** 3 / 3.0 + 2.0 * n ** 2
+
+
+FP64_PEAK_TFLOPS = 37.2  # DFMA throughput measured on this part with tools/ubench_fp64.cu (MEASURED_PEAKS.json has no FP64 figure)
+
+
 def ncu_traffic(kernel, nw, workload):
     """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture
     (profiles/ncu_traffic.json: {"<workload>x<windows>": {"<kernel>": bytes}}), or None."""
@@ -159,26 +191,35 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def config_of(w, name, nw):
+    """`config` of the JSON line: the SAME dict in both arms (the driver compares it)."""
+    return {"workload": workload_desc(w, name, nw)}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the dependency-free restatement of the reference's g2o path (the reference itself cannot be
-    compiled here: Eigen/OpenCV/CHOLMOD are absent), on all host threads the workload can use: one window
-    per thread (each optimisation is single-threaded like the reference's)."""
+    compiled here: Eigen/OpenCV/CHOLMOD are absent; its SO3 / pre-integration part is pinned against the compiled
+    reference, tests/test_oracle_vs_ref.py), on all host threads the workload can use: one window per thread (each
+    optimisation is single-threaded like the reference's).  One step = one window solve on every thread: a bounded
+    sample of the workload (a 20-KF window is ~0.3 s on one core)."""
     if rank != 0:
         return
     from mc_slam_b200 import synth
     nw = args.windows
     threads = 1 if nw == 1 else min(host_threads(), nw)
     wins = [synth.make_config(args.workload, window_index=i) for i in range(min(nw, max(threads, 1)))]
-    steps = max(1, min(args.steps, 4))  # bounded sample: one window solve is ~0.3 s on one core
-    val, n_solved, iters, edges, wall = cpu_throughput(wins, threads, steps)
+    W, K = max(0, args.warmup), max(1, args.steps)
+    if W:
+        cpu_throughput(wins, threads, min(W, 2))
+    val, n_solved, iters, edges, wall = cpu_throughput(wins, threads, K)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(wins[0], args.workload, nw), "threads": threads},
+        "config": config_of(wins[0], args.workload, nw),
         "edges_linearized_per_sec": edges / wall if threads > 1 else None,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_solved} window solves ({steps} per thread) of the same workload, "
+                         "sample": f"{n_solved} window solves ({K} steps of one window per thread) of the same workload, "
                                    f"oracle/libvilba_oracle.so, {threads} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -202,6 +243,7 @@ def main():
     ap.add_argument("--windows", type=int, default=64, help="independent windows per GPU solved as one batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 1 / 2 / 4 sections")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -320,6 +362,118 @@ def main():
                   "note": "ONE 20-KF window per call (BASELINE config 3): L2-resident and latency-bound"}
         c1.close()
 
+    # ---- BASELINE configs 1, 2, 4 on one GPU, and config 4 point-sharded over the ranks ---------------------
+    def one_window(name, k):
+        """resident + end-to-end LM iterations/s of ONE window of config `name` (non-sharded path)."""
+        w = synth.make_config(name)
+        c = api.Context(local_rank)
+        c.upload_batch([w])
+        timed_resident(c, 2)
+        ms, it, ed = timed_resident(c, k)
+        pr = c.prepare([w])
+        pr.run()
+        t_e2e, it_e2e = 0.0, 0
+        for _ in range(k):
+            flush_l2()
+            t0 = time.perf_counter()
+            pr.run()
+            t_e2e += time.perf_counter() - t0
+            it_e2e += len(pr.collect()[0].trace)
+        c.reset_stats()
+        c.set_profiling(True)
+        timed_resident(c, 1)
+        sp = c.stats()
+        c.set_profiling(False)
+        c.close()
+        per = lambda ms_, n_: 1e3 * ms_ / max(1, n_)  # noqa: E731
+        return w, {"workload": workload_desc(w, name, 1), "value": it / (ms * 1e-3), "unit": UNIT, "ms_per_solve": ms / k,
+                   "ms_per_iter": ms / max(1, it), "edges_linearized_per_sec": ed / (ms * 1e-3),
+                   "e2e": it_e2e / t_e2e, "e2e_ms_per_solve": 1e3 * t_e2e / k,
+                   "kernels_us": {"linearize": per(sp.linearize_ms, sp.linearize_launches), "schur": per(sp.schur_ms, sp.schur_launches),
+                                  "chol_solve": per(sp.solve_ms, sp.solve_launches), "update_eval": per(sp.update_ms, sp.update_launches)}}
+
+    extra = {}
+    if world == 1 and not args.no_extra and args.workload == "c3" and nw > 1:
+        _, extra["c1"] = one_window("c1", max(3, min(K, 10)))
+        _, extra["c4"] = one_window("c4", 3)
+        # config 2: 4096 key-frame pairs x 40 samples, inputs resident (device pointers) and end to end (host buffers)
+        b = synth.make_imu_batch(n_pairs=4096, n_samples=40)
+        dev = torch.device("cuda", local_rank)
+        t_ = lambda a_, dt_=np.float64: torch.from_numpy(np.ascontiguousarray(a_, dt_).reshape(-1)).to(dev)  # noqa: E731
+        sb, g_, a_, d_, bg_, ba_ = t_(b.sample_begin, np.int32), t_(b.gyro), t_(b.acc), t_(b.dt), t_(b.bg), t_(b.ba)
+        o_ = torch.empty(4096 * 142, dtype=torch.float64, device=dev)
+        cp = api.Context(local_rank)
+        run_p = lambda: cp.preintegrate_batch_dev(4096, 4096 * 40, sb.data_ptr(), g_.data_ptr(), a_.data_ptr(), d_.data_ptr(),  # noqa: E731
+                                                  bg_.data_ptr(), ba_.data_ptr(), o_.data_ptr())
+        for _ in range(3):
+            run_p()
+        cp.reset_stats()
+        cp.set_profiling(True)
+        for _ in range(20):
+            flush_l2()
+            run_p()
+        sp = cp.stats()
+        cp.set_profiling(False)
+        p_us = 1e3 * sp.preint_ms / max(1, sp.preint_launches)
+        cp.preintegrate_batch(b.sample_begin, b.gyro, b.acc, b.dt, b.bg, b.ba)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            cp.preintegrate_batch(b.sample_begin, b.gyro, b.acc, b.dt, b.bg, b.ba)
+        p_e2e = (time.perf_counter() - t0) / 5
+        cp.close()
+        p_bytes = 4096 * 40 * 56 + 4096 * (48 + 1136)  # SURVEY 8(d) B_pre
+        p_flops = 4096 * 40 * 600.0
+        peak_, _ = _peaks()
+        extra["c2_preint"] = {
+            "workload": "c2: 4096 key-frame pairs x 40 IMU samples (200 Hz), covariance + bias Jacobians",
+            "pairs_per_sec": 4096 / (p_us * 1e-6), "updates_per_sec": 4096 * 40 / (p_us * 1e-6), "ms": p_us * 1e-3,
+            "e2e_pairs_per_sec": 4096 / p_e2e, "e2e_ms": 1e3 * p_e2e,
+            "roofline": {"kernel": "preint_batch_kernel", "bound": "fp64 latency", "algorithmic_bytes": p_bytes,
+                         "achieved_gbs": p_bytes / (p_us * 1e-6) / 1e9, "frac_hbm": p_bytes / (p_us * 1e-6) / 1e9 / peak_,
+                         "achieved_tflops": p_flops / (p_us * 1e-6) / 1e12, "frac_fp64": p_flops / (p_us * 1e-6) / 1e12 / FP64_PEAK_TFLOPS},
+            "timing": "CUDA events on the library stream around the kernel, 20 launches, L2 flushed in between"}
+
+    # config 4 sharded by map point over the ranks of this run (at N = 1: the collective path with one rank)
+    sharded = None
+    if not args.no_extra and args.workload == "c3" and nw > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+        if world > 1:
+            dist.broadcast(uid, 0)
+        cs = api.Context(local_rank)
+        cs.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        w4 = synth.make_config("c4")
+        sub, p0, p1, e0, e1 = sharding.shard_window(w4, rank, world)
+        s_ms, s_it = 0.0, 0
+        for it_ in range(1 + 3):
+            barrier()
+            r4 = cs.local_ba(sub)
+            if it_ >= 1:
+                s_ms += r4.solve_ms
+                s_it += len(r4.trace)
+        cs.reset_stats()
+        cs.set_profiling(True)
+        barrier()
+        r4 = cs.local_ba(sub)
+        sp = cs.stats()
+        cs.set_profiling(False)
+        (s_ms_max,), _ = sharding.reduce_bench([s_ms], [0.0], device="cuda")
+        n4 = 15 * w4.n_free
+        lds4 = (n4 + 3) & ~3
+        sharded = {
+            "workload": workload_desc(w4, "c4", 1) + f", map points sharded over {world} rank(s)",
+            "lm_iters_per_sec": s_it / (s_ms_max * 1e-3), "ms_per_iter": s_ms_max / max(1, s_it), "ms_per_solve": s_ms_max / 3,
+            "edges_per_rank": int(e1 - e0), "points_per_rank": int(p1 - p0),
+            "nccl_calls_per_slot": 4,
+            "allreduce_bytes_per_slot": int(8 * (n4 * n4 + n4) + 8 + 8 * (lds4 * n4 + n4) + 16),
+            "chol_ms": sp.solve_ms / max(1, sp.solve_launches), "schur_ms": sp.schur_ms / max(1, sp.schur_launches),
+            "linearize_ms": sp.linearize_ms / max(1, sp.linearize_launches),
+            "note": "one slot = linearise-if-needed + one LM trial; allreduce(sum) of H_pp|b_p and of S|b_s, allreduce(max) of "
+                    "max diag H_ll, allreduce(sum) of chi2|scale; the reduced system is solved redundantly on every rank; "
+                    "device time (CUDA events), max over ranks, 3 solves after 1 warm-up; per-kernel times from a profiled solve"}
+        cs.close()
+
     # ---- reduce over ranks ----------------------------------------------------------------------------
     (dev_ms_max, e2e_s_max), (iters_all, e2e_iters_all, edges_all, launches_all) = sharding.reduce_bench(
         [dev_ms, e2e_s], [float(iters), float(e2e_iters), float(edges), float(st.kernel_launches)], device="cuda")
@@ -327,22 +481,41 @@ def main():
     if rank == 0:
         peak, peak_src = _peaks()
         n_red = 15 * wins[0].n_free
+        per = lambda ms_, n_: 1e3 * ms_ / max(1, n_)  # noqa: E731
+        lin_us, schur_us = per(stp.linearize_ms, stp.linearize_launches), per(stp.schur_ms, stp.schur_launches)
+        chol_us, upd_us = per(stp.solve_ms, stp.solve_launches), per(stp.update_ms, stp.update_launches)
         b_lin = sum(algorithmic_bytes_linearize(w) for w in wins) / groups
-        lin_us = 1e3 * stp.linearize_ms / max(1, stp.linearize_launches)
-        chol_us = 1e3 * stp.solve_ms / max(1, stp.solve_launches)
-        schur_us = 1e3 * stp.schur_ms / max(1, stp.schur_launches)
-        achieved = b_lin / (lin_us * 1e-6) / 1e9 if lin_us > 0 else 0.0
+        b_schur = sum(algorithmic_bytes_schur(w) for w in wins) / groups
+        b_upd = sum(algorithmic_bytes_update(w) for w in wins) / groups
+        f_chol = sum(solve_flops(w) for w in wins) / groups
+        gbs = lambda b_, us_: b_ / (us_ * 1e-6) / 1e9 if us_ > 0 else 0.0  # noqa: E731
+        lane_w = nw // groups
+        roofline_all = [
+            {"kernel": "linearize_v2 + reduce_partials + assemble_hpp (linearize_imu_v2 beside it)", "bound": "hbm",
+             "bytes": int(b_lin), "us": lin_us, "achieved": gbs(b_lin, lin_us), "unit": "GB/s", "frac": gbs(b_lin, lin_us) / peak,
+             "traffic": ncu_traffic("linearize_v2_kernel", lane_w, args.workload)},
+            {"kernel": "schur_rec + schur_tile + schur_finish", "bound": "hbm", "bytes": int(b_schur), "us": schur_us,
+             "achieved": gbs(b_schur, schur_us), "unit": "GB/s", "frac": gbs(b_schur, schur_us) / peak,
+             "traffic": ncu_traffic("schur_tile_kernel", lane_w, args.workload)},
+            {"kernel": "chol_la (reduced-system LDL^T + solve)", "bound": "fp64", "flops": f_chol, "us": chol_us,
+             "achieved": f_chol / (max(1e-9, chol_us) * 1e-6) / 1e12, "unit": "TFLOP/s",
+             "frac": f_chol / (max(1e-9, chol_us) * 1e-6) / 1e12 / FP64_PEAK_TFLOPS, "traffic": None},
+            {"kernel": "update_eval (oplus + landmark back-substitution + residuals)", "bound": "hbm", "bytes": int(b_upd),
+             "us": upd_us, "achieved": gbs(b_upd, upd_us), "unit": "GB/s", "frac": gbs(b_upd, upd_us) / peak,
+             "traffic": ncu_traffic("update_eval_kernel", lane_w, args.workload)},
+        ]
+        dom = max(roofline_all, key=lambda r_: r_["us"])
         ws_mb = nw * 21 if args.workload == "c3" else None
         line = {
             "metric": METRIC, "value": iters_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(wins[0], args.workload, nw),
-                       "l2": "flushed (256 MiB write) between steps" + (f"; working set ~{ws_mb} MB per GPU" if ws_mb else ""),
-                       "windows_per_gpu": nw, "lanes": groups,
-                       "parallelism": f"independent windows, {nw} per GPU x {world} GPUs, no collective; per GPU {groups} "
-                                      f"concurrent lanes of ~{nw // groups} windows, one batched launch per kernel and lane",
-                       "timing": "CUDA events on the library stream around each batched solve, summed over steps, max over ranks"},
+            "config": config_of(wins[0], args.workload, nw),
+            "run": {"l2": "flushed (256 MiB write) between steps" + (f"; working set ~{ws_mb} MB per GPU" if ws_mb else ""),
+                    "windows_per_gpu": nw, "lanes": groups,
+                    "parallelism": f"independent windows, {nw} per GPU x {world} GPUs, no collective; per GPU {groups} "
+                                   f"concurrent lanes of ~{nw // groups} windows, one batched launch per kernel and lane",
+                    "timing": "CUDA events on the library stream around each batched solve, summed over steps, max over ranks"},
             "edges_linearized_per_sec": edges_all / (dev_ms_max * 1e-3),
             "windows_per_sec": nw * world * K / (dev_ms_max * 1e-3),
             "lm_iters_per_step": iters / K,
@@ -352,22 +525,26 @@ def main():
                     "call": "vilba_local_ba_batch (host buffers in and out)" if nw > 1 else "vilba_local_ba"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"kernel": "linearize_v2_kernel + reduce_partials + assemble_hpp (linearize_imu_v2 beside it)",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("linearize_v2_kernel", nw // groups, args.workload),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(b_lin),
-                         "avg_launch_us": lin_us,
-                         "note": "linearize+accumulate (the kernels the north star names) over the windows of one lane; "
-                                 "algorithmic bytes = SURVEY 8(d) B_lin summed over those windows; launch time from a pass "
-                                 "that runs the lanes one after the other; traffic = dram read+write of linearize_v2_kernel "
-                                 "per launch from the committed ncu --set full capture"},
-            "kernels_us": {"linearize": lin_us, "schur": schur_us, "chol_solve": chol_us,
+            # the dominant kernel group of the timed configuration (largest device time per slot of one lane)
+            "roofline": {"kernel": dom["kernel"], "bound": "hbm" if dom["bound"] == "hbm" else "tensor",
+                         "achieved": dom["achieved"], "peak": peak if dom["bound"] == "hbm" else FP64_PEAK_TFLOPS,
+                         "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom.get("bytes"), "avg_launch_us": dom["us"],
+                         "note": "algorithmic bytes = SURVEY 8(d) formula summed over the windows of one lane (one launch covers a "
+                                 "lane); launch time = CUDA events between the kernel groups in a pass that runs the lanes "
+                                 "concurrently like the timed pass (graphs off); traffic = dram read+write per launch from the "
+                                 "committed ncu --set full capture (profiles/ncu_traffic.json)"
+                                 + ("" if dom["bound"] == "hbm" else "; FP64 CUDA-core kernel: peak = measured DFMA throughput, "
+                                    "reported under the contract's 'tensor' label (no tensor cores are used)")},
+            "roofline_all": roofline_all,
+            "linearize_accumulate_frac_hbm": roofline_all[0]["frac"],
+            "kernels_us": {"linearize": lin_us, "schur": schur_us, "chol_solve": chol_us, "update_eval": upd_us,
                            "note": "per batched launch of one lane; CUDA events around each kernel group in a second, ungraphed pass "
-                                   "that runs the lanes one after the other"},
-            "chol": {"kernel": "chol_cluster_kernel", "bound": "fp64 dependent-issue latency",
-                     "achieved_tflops": (nw / groups) * (n_red ** 3 / 3.0 + 2.0 * n_red ** 2) / (1e-6 * max(1e-9, chol_us)) / 1e12,
-                     "peak_tflops": 37.2, "note": "dense Cholesky of the reduced camera systems, one 8-CTA cluster per window"},
+                                   "with the lanes concurrent (the timed configuration)"},
         }
+        line.update(extra)
+        if sharded:
+            line["sharded_c4"] = sharded
         if single:
             line["single_window"] = single
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
@@ -378,9 +555,14 @@ def main():
                                     "sample": f"{n_solved} window solves of the same workload on {threads} host threads, one "
                                               "window per thread (oracle restatement; faster than real g2o's MatrixXd path, "
                                               "so the ratio is conservative)"}
+            v1 = val
             if threads > 1:
                 v1, _, _, _, _ = cpu_throughput(wins[:1], 1, 2)
                 line["cpu_baseline"]["single_thread_value"] = v1
+            if single:
+                single["cpu_single_thread"] = v1
+                single["ratio_vs_cpu_single_thread"] = single["value"] / v1
+                single["e2e_ratio_vs_cpu_single_thread"] = single["e2e"] / v1
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

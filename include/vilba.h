@@ -274,11 +274,17 @@ typedef struct vilba_stats {
     int64_t schur_launches;
     double solve_ms;               /* reduced-system factor + solve                                        */
     int64_t solve_launches;
+    double update_ms;              /* oplus + landmark back-substitution + residual evaluation of a trial  */
+    int64_t update_launches;
+    double preint_ms;              /* pre-integration kernel (vilba_preintegrate_batch[_dev]), profiling on */
+    int64_t preint_launches;
 } vilba_stats;
 
 void vilba_get_stats(const vilba_ctx* ctx, vilba_stats* s);
 void vilba_reset_stats(vilba_ctx* ctx);
-/* when on, per-kernel CUDA-event timing is collected into vilba_stats (adds event records only) */
+/* when on, per-kernel-group CUDA-event timing is collected into vilba_stats: the slot kernels are launched one by one
+ * instead of through the CUDA graph (events in between); the lanes of a split batch still run concurrently, i.e. in the
+ * configuration that is timed without profiling */
 void vilba_set_profiling(vilba_ctx* ctx, int on);
 
 #ifdef __cplusplus

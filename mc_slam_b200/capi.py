@@ -138,6 +138,10 @@ class Stats(C.Structure):
         ("schur_launches", C.c_int64),
         ("solve_ms", C.c_double),
         ("solve_launches", C.c_int64),
+        ("update_ms", C.c_double),
+        ("update_launches", C.c_int64),
+        ("preint_ms", C.c_double),
+        ("preint_launches", C.c_int64),
     ]
 
 

@@ -189,6 +189,9 @@ struct vilba_ctx {
     size_t in_total = 0, out_total = 0, lm_base = 0, out_region = 0;  // arena: [in | out | lm array | work]
     LaunchDims dims;
     int chol_cluster = 8;
+    int preint_group = 0;            // env VILBA_PREINT_GROUP: 0 = scan kernel, lanes per pair chosen from the average interval length;
+                                     // -8/-16/-32 = scan kernel with that many lanes per pair; 8/16/32 = the sequential
+                                     // entry-parallel kernel
     int chol_la_mode = 1;            // env VILBA_CHOL_LA: 0 never, 1 automatic, 2 always (when the tiles fit)
     int chol_big_above = 480;        // env VILBA_CHOL_BIG_ABOVE: reduced systems larger than this use chol_big.cu (the cluster
                                      // kernel's panel + row stage fit in shared memory up to n = 508)
@@ -312,7 +315,10 @@ void probe_drain(vilba_ctx* ctx) {
             ctx->stats.schur_ms += sch, ctx->stats.schur_launches++;
             ctx->stats.solve_ms += chol, ctx->stats.solve_launches++;
             if (cudaEventElapsedTime(&t, p[2], p[6]) == cudaSuccess) ctx->dbg_ms[1] += t;  // schur_prep alone
-            if (cudaEventElapsedTime(&t, p[4], p[5]) == cudaSuccess) ctx->dbg_ms[2] += t;  // update_eval alone
+            if (cudaEventElapsedTime(&t, p[4], p[5]) == cudaSuccess) {  // update_eval alone
+                ctx->dbg_ms[2] += t;
+                ctx->stats.update_ms += t, ctx->stats.update_launches++;
+            }
         }
     }
     ctx->probes_used = 0;
@@ -918,6 +924,8 @@ void add_stats(vilba_stats& a, const vilba_stats& b) {
     a.linearize_ms += b.linearize_ms, a.linearize_launches += b.linearize_launches;
     a.schur_ms += b.schur_ms, a.schur_launches += b.schur_launches;
     a.solve_ms += b.solve_ms, a.solve_launches += b.solve_launches;
+    a.update_ms += b.update_ms, a.update_launches += b.update_launches;
+    a.preint_ms += b.preint_ms, a.preint_launches += b.preint_launches;
 }
 
 // ---- a batch split over lanes ---------------------------------------------------------------------
@@ -992,8 +1000,9 @@ int solve_split(vilba_ctx* ctx, vilba_result* out) {
         ctx->lanes[l]->start_after = ctx->ev_a;
         ctx->lanes[l]->profiling = ctx->profiling;
     }
-    // profiling pass: one lane after the other, so that the per-kernel times are those of the kernels alone
-    int r = for_each_lane(ctx, lanes, !ctx->profiling, [&](int l) {
+    // (a profiling pass keeps the lanes concurrent: the per-kernel-group times are those of the timed configuration,
+    // contention between the lanes included)
+    int r = for_each_lane(ctx, lanes, true, [&](int l) {
         return solve_batch(ctx->lanes[l], out + ctx->split_first[l], nullptr);
     });
     for (int l = 0; l < lanes; ++l) {
@@ -1067,6 +1076,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("VILBA_CHOL_BIG_ABOVE")) ctx->chol_big_above = std::atoi(e);
     if (const char* e = std::getenv("VILBA_CHOL_LA")) ctx->chol_la_mode = std::atoi(e);
+    if (const char* e = std::getenv("VILBA_PREINT_GROUP")) ctx->preint_group = std::atoi(e);
     if (const char* e = std::getenv("VILBA_SCHUR")) ctx->schur_gather_only = std::strcmp(e, "gather") == 0;
     if (const char* e = std::getenv("VILBA_SP_GRID")) ctx->sp_grid_cap = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_SP_SETS")) ctx->sp_sets = std::max(1, std::atoi(e));
@@ -1287,11 +1297,23 @@ int vilba_preintegrate_batch_dev(vilba_ctx* ctx, int32_t n_pairs, int32_t n_samp
                                  const double* gyro_dev, const double* acc_dev, const double* dt_dev,
                                  const double* bg_dev, const double* ba_dev, double* out_dev) {
     if (!ctx || n_pairs < 0) return VILBA_ERR_ARG;
-    (void)n_samples;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (ctx->profiling) CK(cudaEventRecord(ctx->ev_a, ctx->stream), "event");
+    int group = ctx->preint_group;
+    if (group == 0 && n_pairs > 0) {  // tiles of G samples: short intervals waste fewer lanes with small groups
+        const int avg = n_samples / n_pairs;
+        group = avg <= 64 ? -8 : (avg <= 160 ? -16 : -32);
+    }
     CK(launch_preint_batch(ctx->stream, n_pairs, sample_begin_dev, gyro_dev, acc_dev, dt_dev, bg_dev, ba_dev, out_dev,
-                           ctx->prm.gyr_meas_cov, ctx->prm.acc_meas_cov, 8), "preint_batch");
+                           ctx->prm.gyr_meas_cov, ctx->prm.acc_meas_cov, group), "preint_batch");
     ctx->stats.kernel_launches += n_pairs > 0 ? 1 : 0;
+    if (ctx->profiling) {  // device time of the kernel alone, CUDA events on the launching stream
+        CK(cudaEventRecord(ctx->ev_b, ctx->stream), "event");
+        CK(cudaEventSynchronize(ctx->ev_b), "sync");
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b), "elapsed");
+        ctx->stats.preint_ms += ms, ctx->stats.preint_launches++;
+    }
     return VILBA_OK;
 }
 
