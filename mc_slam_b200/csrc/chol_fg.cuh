@@ -149,4 +149,96 @@ __device__ __forceinline__ void rowsolve_hi(double (&hi)[16], const double* __re
     }
 }
 
+// Back substitution M^T x = yf for a factor stored as (a) the rows below the 32-wide diagonal blocks, row-major in Lf
+// (Lf[r * ld + c] = M(r, c)), and (b) the inverse of every diagonal block (Minv[blk][r * 32 + c], row-major), block by
+// block from the last one:  x_k = Minv_k^T (yf_k - sum over the rows r below the block of M(r, block)^T x_r).
+// One CTA of NT threads: its warps split the rows below (lane = column of the block: 256-byte coalesced row segments,
+// the first 16 rows per warp fetched one block ahead so that L2 latency is off the chain), their partial sums meet in
+// shared memory, warp 0 applies the inverse -- no per-unknown chain.  smem: backsub_smem_doubles(n, NT) doubles.
+__host__ __device__ constexpr int backsub_smem_doubles(int n, int nt) { return 2 * 32 * 32 + (nt / 32 + 1) * 32 + n + 32; }
+
+template <int NT>
+__device__ __forceinline__ void backsub_blocks(int n, int ld, const double* __restrict__ Lf, const double* __restrict__ Minv_g,
+                                               const double* __restrict__ yf, double* __restrict__ xout, double* smem) {
+    constexpr int NB = 32, NW = NT / 32, MV = (NB * NB / 2 + NT - 1) / NT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = (n + NB - 1) / NB;
+    double* Mi = smem;                  // [2][NB*NB] inverse of the current / next diagonal block
+    double* part = Mi + 2 * NB * NB;    // [NW][NB] partial sums
+    double* ts = part + NW * NB;        // [NB]
+    double* xs = ts + NB;               // [n + NB]
+    auto fetch_rows = [&](int blk, double (&v)[16]) {
+        const int c = blk * NB + lane;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = (blk + 1) * NB + warp + NW * i;
+            v[i] = (r < n && c < n) ? __ldcg(Lf + (size_t)r * ld + c) : 0.0;
+        }
+    };
+    double cur[16], nxt[16];
+    double2 mnext[MV];
+    fetch_rows(nblk - 1, cur);
+    {
+        const double2* m = reinterpret_cast<const double2*>(Minv_g + (size_t)(nblk - 1) * NB * NB);
+        double2* dst = reinterpret_cast<double2*>(Mi + ((nblk - 1) & 1) * NB * NB);
+        for (int i = tid; i < NB * NB / 2; i += NT) dst[i] = __ldcg(m + i);
+    }
+    __syncthreads();
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int j0 = blk * NB, jb = min(NB, n - j0);
+        if (blk > 0) {  // next block's rows and inverse: in flight during this block's reduction
+            fetch_rows(blk - 1, nxt);
+            const double2* m = reinterpret_cast<const double2*>(Minv_g + (size_t)(blk - 1) * NB * NB);
+#pragma unroll
+            for (int i = 0; i < MV; ++i)
+                if (tid + NT * i < NB * NB / 2) mnext[i] = __ldcg(m + tid + NT * i);
+        }
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const int r = j0 + NB + warp + NW * i;
+            s0 = fma(cur[i], (r < n) ? xs[r] : 0.0, s0);
+            s1 = fma(cur[i + 1], (r + NW < n) ? xs[r + NW] : 0.0, s1);
+        }
+        if (j0 + lane < n) {  // systems with more than 16 NW rows below a block: the rest straight from L2, 4 in flight
+            int r = j0 + NB + warp + NW * 16;
+            for (; r + 3 * NW < n; r += 4 * NW) {
+                const double l0 = __ldcg(Lf + (size_t)r * ld + j0 + lane), l1 = __ldcg(Lf + (size_t)(r + NW) * ld + j0 + lane);
+                const double l2 = __ldcg(Lf + (size_t)(r + 2 * NW) * ld + j0 + lane), l3 = __ldcg(Lf + (size_t)(r + 3 * NW) * ld + j0 + lane);
+                s0 = fma(l0, xs[r], s0), s1 = fma(l1, xs[r + NW], s1), s0 = fma(l2, xs[r + 2 * NW], s0), s1 = fma(l3, xs[r + 3 * NW], s1);
+            }
+            for (; r < n; r += NW) s0 = fma(__ldcg(Lf + (size_t)r * ld + j0 + lane), xs[r], s0);
+        }
+        part[warp * NB + lane] = s0 + s1;
+        __syncthreads();
+        if (warp == 0) {
+            double t = (lane < jb) ? __ldcg(yf + j0 + lane) : 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) t -= part[w2 * NB + lane];
+            ts[lane] = t;
+            __syncwarp();
+            const double* m = Mi + (blk & 1) * NB * NB;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r += 4) {
+                a0 = fma(m[r * NB + lane], ts[r], a0);
+                a1 = fma(m[(r + 1) * NB + lane], ts[r + 1], a1);
+                a2 = fma(m[(r + 2) * NB + lane], ts[r + 2], a2);
+                a3 = fma(m[(r + 3) * NB + lane], ts[r + 3], a3);
+            }
+            xs[j0 + lane] = (lane < jb) ? (a0 + a1) + (a2 + a3) : 0.0;
+        }
+        if (blk > 0) {
+            double2* dst = reinterpret_cast<double2*>(Mi + ((blk - 1) & 1) * NB * NB);
+#pragma unroll
+            for (int i = 0; i < MV; ++i)
+                if (tid + NT * i < NB * NB / 2) dst[tid + NT * i] = mnext[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+    }
+    for (int i = tid; i < n; i += NT) xout[i] = xs[i];
+}
+
 }  // namespace vilba

@@ -97,7 +97,7 @@ struct LaLayout {
         const int srow = jobs < kLaWorkers ? jobs : kLaWorkers;
         const int rows = prow > srow ? prow : srow;
         const int work = rows * kLDP + nt * 16 * kLaWorkers;   // panel + tiles ...
-        const int back = 2 * kNB * kNB + (kLaThreads / 32 + 1) * kNB + n + kNB;  // ... reused by the back substitution
+        const int back = backsub_smem_doubles(n, kLaThreads);          // ... reused by the back substitution
         tl = pn + rows * kLDP;
         total = pn + (work > back ? work : back);
     }
@@ -463,66 +463,7 @@ __device__ __forceinline__ void chol_la_body(const CholJob& J, double* smem) {
     // ---------------------------------------------------------------------------------------------
     if (crank != 0) return;
     LA_T0B();
-    constexpr int NW = kLaThreads / 32;
-    double* Mi = Pn;                    // [2][NB*NB] inverse of the current / next diagonal block
-    double* part = Mi + 2 * NB * NB;    // [NW][NB] partial sums
-    double* ts = part + NW * NB;        // [NB]
-    double* xs = ts + NB;               // [n + NB]
-    auto fetch_rows = [&](int blk, double (&v)[16]) {
-        const int c = blk * NB + lane;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int r = (blk + 1) * NB + warp + NW * i;
-            v[i] = (r < n && c < n) ? __ldcg(J.Lf + (size_t)r * ld + c) : 0.0;
-        }
-    };
-    double cur[16], nxt[16];
-    double2 mnext = make_double2(0.0, 0.0);
-    fetch_rows(nblk - 1, cur);
-    {
-        const double2* m = reinterpret_cast<const double2*>(Minv_g + (size_t)(nblk - 1) * NB * NB);
-        reinterpret_cast<double2*>(Mi + ((nblk - 1) & 1) * NB * NB)[tid] = __ldcg(m + tid);
-    }
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-        const int j0 = blk * NB, jb = min(NB, n - j0);
-        if (blk > 0) {  // next block's rows and inverse: in flight during this block's reduction
-            fetch_rows(blk - 1, nxt);
-            mnext = __ldcg(reinterpret_cast<const double2*>(Minv_g + (size_t)(blk - 1) * NB * NB) + tid);
-        }
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-            const int r = j0 + NB + warp + NW * i;
-            s0 = fma(cur[i], (r < n) ? xs[r] : 0.0, s0);
-            s1 = fma(cur[i + 1], (r + NW < n) ? xs[r + NW] : 0.0, s1);
-        }
-        for (int r = j0 + NB + warp + NW * 16; r < n; r += NW)  // systems with more than 256 rows below a block
-            if (j0 + lane < n) s0 = fma(__ldcg(J.Lf + (size_t)r * ld + j0 + lane), xs[r], s0);
-        part[warp * NB + lane] = s0 + s1;
-        __syncthreads();
-        if (warp == 0) {
-            double t = (lane < jb) ? __ldcg(yf + j0 + lane) : 0.0;
-#pragma unroll
-            for (int w2 = 0; w2 < NW; ++w2) t -= part[w2 * NB + lane];
-            ts[lane] = t;
-            __syncwarp();
-            const double* m = Mi + (blk & 1) * NB * NB;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-            for (int r = 0; r < NB; r += 4) {
-                a0 = fma(m[r * NB + lane], ts[r], a0);
-                a1 = fma(m[(r + 1) * NB + lane], ts[r + 1], a1);
-                a2 = fma(m[(r + 2) * NB + lane], ts[r + 2], a2);
-                a3 = fma(m[(r + 3) * NB + lane], ts[r + 3], a3);
-            }
-            xs[j0 + lane] = (lane < jb) ? (a0 + a1) + (a2 + a3) : 0.0;
-        }
-        if (blk > 0) reinterpret_cast<double2*>(Mi + ((blk - 1) & 1) * NB * NB)[tid] = mnext;
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
-    }
-    for (int i = tid; i < n; i += kLaThreads) J.x[i] = xs[i];
+    backsub_blocks<kLaThreads>(n, ld, J.Lf, Minv_g, yf, J.x, Pn);
     if (tid == 0) *J.fail = s_fail;
 #ifdef VILBA_LA_TIMING
     if (J.dbg && tid == 0) J.dbg[11] = clock64() - tb_;  // back substitution

@@ -23,7 +23,7 @@ extern "C" int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S
     if (cudaSetDevice(device) != cudaSuccess) return VILBA_ERR_NO_DEVICE;
     const int ld = (n + 3) & ~3;
     const size_t mat = (size_t)ld * n;
-    const size_t scr = std::max<size_t>(chol_la_scratch_doubles(n), (size_t)256 * (n / 16 + 2));
+    const size_t scr = std::max<size_t>(std::max<size_t>(chol_la_scratch_doubles(n), (size_t)256 * (n / 16 + 2)), chol_big_scratch_doubles(n));
     // per window: S | bs | x | Lfac | cminv | cdinv, then pristine S | b shared by all windows
     const size_t per_win = 2 * mat + 3 * (size_t)ld + scr + 64;  // the last 64: debug counters
     double* dev = nullptr;

@@ -213,6 +213,7 @@ size_t schur_partial_doubles(int n_free);
 bool chol_has_stage(int n_cap);
 int chol_block_size(int n_cap);
 cudaError_t configure_chol_big(int n_cap);
+size_t chol_big_scratch_doubles(int n);  // DevWindow::cminv must hold this many doubles when chol_big.cu is used
 // look-ahead cluster kernel with the trailing matrix in shared memory (chol_la.cu)
 int chol_la_tiles_per_thread(int n, int cluster);
 size_t chol_la_smem_bytes(int n, int cluster);

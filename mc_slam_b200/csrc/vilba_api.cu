@@ -150,7 +150,8 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bo
     L.bs = take(sizeof(double) * n);  // directly behind S: one allreduce covers S | b_s of a sharded window
     L.s_span = L.bs + sizeof(double) * n - L.S;
     L.Lfac = take(sizeof(double) * lds * n);
-    L.cminv = take(sizeof(double) * std::max<size_t>(256 * (n / 16 + 2), chol_la_scratch_doubles((int)n)));
+    L.cminv = take(sizeof(double) * std::max<size_t>(std::max<size_t>(256 * (n / 16 + 2), chol_la_scratch_doubles((int)n)),
+                                                     chol_big_scratch_doubles((int)n)));
     L.cdinv = take(sizeof(double) * n);
     L.x = take(sizeof(double) * n);
     L.dbg = take(sizeof(long long) * 16);

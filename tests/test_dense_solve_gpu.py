@@ -69,6 +69,26 @@ def test_indefinite_system_is_factored_through_like_simplicial_ldlt(n):
     assert fail == 0 and rel_err(S, b, batch_x) < 1e-8
 
 
+@pytest.mark.parametrize("n", [100, 600, 1485])
+def test_whole_gpu_kernel_factors_an_indefinite_system_through(n):
+    rng = np.random.default_rng(11 + n)
+    S, b = spd(n, 500 + n, cond=1e3)
+    d = np.ones(n)
+    d[rng.choice(n, size=max(2, n // 10), replace=False)] = -1.0
+    low = np.linalg.cholesky(S)
+    S = (low * d) @ low.T
+    S = 0.5 * (S + S.T)
+    x, fail, _ = capi.diag_dense_solve(S, b, variant=2, cluster=1)
+    assert fail == 0 and rel_err(S, b, x) < 1e-8
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 63, 64, 65, 127, 129])
+def test_whole_gpu_kernel_on_tile_edges(n):
+    S, b = spd(n, 600 + n, cond=1e4)
+    x, fail, _ = capi.diag_dense_solve(S, b, variant=2, cluster=1)
+    assert fail == 0 and rel_err(S, b, x) < 1e-9
+
+
 def test_zero_pivot_raises_the_failure_flag():
     S, b = spd(64, 9)
     S[0, :] = 0.0
