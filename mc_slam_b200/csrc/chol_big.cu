@@ -45,26 +45,11 @@ size_t chol_big_scratch_doubles(int n) { return big_minv_doubles(n) + (size_t)((
 
 __device__ __forceinline__ void bar_grp(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-// One warp: inverse of a 32 x 32 diagonal factor block M = Lu |D|^1/2 (unit-lower Lu given transposed in Dt) into
-// out[r * 32 + c], row-major: a row e_j of the identity solved against Lu^T is column j of Lu^-1.
-__device__ __forceinline__ void invert_block(const double* __restrict__ Dt, const double* __restrict__ dab, double* __restrict__ out,
-                                             double* scr /* 32 * 17 */, int lane) {
-    double lo[16], hi[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) lo[c] = (c == lane) ? 1.0 : 0.0, hi[c] = (16 + c == lane) ? 1.0 : 0.0;
-    rowsolve_lo(lo, Dt);
-    double* my = scr + lane * 17;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        my[c] = lo[c];
-        out[c * 32 + lane] = lo[c] * dab[c];
-    }
-    rowsolve_hi(hi, my, Dt);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) out[(16 + c) * 32 + lane] = hi[c] * dab[16 + c];
-}
+// Code size matters in these kernels: every launch starts with a cold instruction cache and the unrolled register
+// kernels (fg4_factor ~1.5 k instructions, a row solve ~0.9 k) are executed once or twice per launch by a few warps, so
+// each of them is instantiated ONCE per kernel and reached through a loop (second pass: warm) or by several warps at once.
 
-// diagonal tile k: 128 threads = one factor group
+// diagonal tile k: 128 threads = one factor group; pass 0 = block A, pass 1 = block B
 __global__ void __launch_bounds__(128) bigchol_diag_kernel(const DevWindow* __restrict__ wp, int k) {
     const DevWindow* w = wp + blockIdx.y;
     if (w->lm->phase != PH_TRIAL) return;
@@ -72,88 +57,85 @@ __global__ void __launch_bounds__(128) bigchol_diag_kernel(const DevWindow* __re
     if (k >= big_tiles(n)) return;
     const int k0 = k * kBT, nb = min(kBT, n - k0);
     const int jbA = min(32, nb), jbB = nb - jbA;
-    __shared__ __align__(16) double DtA[1024], DtB[1024], XdT[32 * kXS34], Fgs[kFgScratch], Scr[32 * 17], Sc[6 * 32];
+    __shared__ __align__(16) double Dt[2][1024], XdT[32 * kXS34], Fgs[kFgScratch], Scr[64 * 17], Sc[6 * 32];
     __shared__ int s_neg[2], s_fail;
     double* const A = w->S;
     double* rec = w->cminv + big_minv_doubles(n) + (size_t)k * kRecDoubles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_fail = 0;
-    double* disA = Sc, *disB = Sc + 32, *dabA = Sc + 64, *dabB = Sc + 96, *sgA = Sc + 128, *sgB = Sc + 160;
-    auto publish = [&](const FgPivots& p, double* dis, double* dab, double* sg, int which) {
+    double* const dis = Sc, *const dab = Sc + 64, *const sg = Sc + 128;  // [2][32] each: block A, block B
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int jb = pass ? jbB : jbA, o = k0 + 32 * pass;
+        // ---- the block (pass 1: updated with the rows solved in pass 0, D' = D - X21 Sigma_A X21^T); lane = row,
+        //      warp = column phase ----
+        double a[2][4];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = 4 * (warp + 4 * sl) + i;
+                a[sl][i] = (lane < jb && c <= lane) ? A[(size_t)(o + c) * ld + o + lane] : (c == lane ? 1.0 : 0.0);
+            }
+        if (pass) {
+            double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+#pragma unroll 4
+            for (int kk = 0; kk < 32; ++kk) {
+                const double own = XdT[kk * kXS34 + lane] * sg[kk];
+                const double2* cp0 = reinterpret_cast<const double2*>(XdT + kk * kXS34 + 4 * warp);
+                const double2* cp1 = reinterpret_cast<const double2*>(XdT + kk * kXS34 + 16 + 4 * warp);
+                const double2 c0a = cp0[0], c0b = cp0[1], c1a = cp1[0], c1b = cp1[1];
+                acc[0][0] = fma(own, c0a.x, acc[0][0]), acc[0][1] = fma(own, c0a.y, acc[0][1]);
+                acc[0][2] = fma(own, c0b.x, acc[0][2]), acc[0][3] = fma(own, c0b.y, acc[0][3]);
+                acc[1][0] = fma(own, c1a.x, acc[1][0]), acc[1][1] = fma(own, c1a.y, acc[1][1]);
+                acc[1][2] = fma(own, c1b.x, acc[1][2]), acc[1][3] = fma(own, c1b.y, acc[1][3]);
+            }
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[sl][i] -= acc[sl][i];
+        }
+        const FgPivots p = fg4_factor(a, lane, warp, Dt[pass], Fgs, 1);
         if (!p.ok) s_fail = 1;
         if (warp == 0) {
             const double sgn = p.d < 0.0 ? -1.0 : 1.0;
             const double isq = 1.0 / sqrt(fabs(p.d));
             const unsigned anyneg = __ballot_sync(0xffffffffu, p.d < 0.0);
-            dis[lane] = isq * sgn, dab[lane] = isq, sg[lane] = sgn;
-            if (lane == 0) s_neg[which] = anyneg != 0;
+            dis[32 * pass + lane] = isq * sgn, dab[32 * pass + lane] = isq, sg[32 * pass + lane] = sgn;
+            if (lane == 0) s_neg[pass] = anyneg != 0;
         }
-    };
-    // ---- block A ----
-    double a[2][4];
+        bar_grp(2);
+        // ---- row solves against this block: pass 0: warp 0 = the rows of block B (-> XdT), warp 1 = the rows of the
+        //      identity (-> inverse of block A for the back substitution).  The inverse of block B is left to the panel
+        //      kernel: nothing in this kernel or the next waits for it ----
+        if (pass == 0 && warp < 2) {
+            const bool inv = warp == 1;
+            double lo[16], hi[16];
 #pragma unroll
-    for (int sl = 0; sl < 2; ++sl)
+            for (int c = 0; c < 16; ++c) {
+                lo[c] = inv ? (c == lane ? 1.0 : 0.0) : ((lane < jbB) ? A[(size_t)(k0 + c) * ld + k0 + 32 + lane] : 0.0);
+                hi[c] = inv ? (16 + c == lane ? 1.0 : 0.0) : ((lane < jbB) ? A[(size_t)(k0 + 16 + c) * ld + k0 + 32 + lane] : 0.0);
+            }
+            double* const my = Scr + tid * 17;
+            const double* scale = inv ? dab : dis;
+            double* out = inv ? w->cminv + (size_t)(2 * k) * 1024 + lane : XdT + lane;
+            const int ostride = inv ? 32 : kXS34;  // Minv[c][j], row-major / XdT[c][row]
+            rowsolve_lo(lo, Dt[0]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = 4 * (warp + 4 * sl) + i;
-            a[sl][i] = (lane < jbA && c <= lane) ? A[(size_t)(k0 + c) * ld + k0 + lane] : (c == lane ? 1.0 : 0.0);
+            for (int c = 0; c < 16; ++c) my[c] = lo[c], out[c * ostride] = lo[c] * scale[c];
+            rowsolve_hi(hi, my, Dt[0]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) out[(16 + c) * ostride] = hi[c] * scale[16 + c];
         }
-    publish(fg4_factor(a, lane, warp, DtA, Fgs, 1), disA, dabA, sgA, 0);
-    bar_grp(2);
-    // ---- rows of block B against block A (warp 0), inverse of block A for the back substitution (warp 1) ----
-    if (warp == 0) {
-        double lo[16], hi[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            lo[c] = (lane < jbB) ? A[(size_t)(k0 + c) * ld + k0 + 32 + lane] : 0.0;
-            hi[c] = (lane < jbB) ? A[(size_t)(k0 + 16 + c) * ld + k0 + 32 + lane] : 0.0;
-        }
-        double* const my = Fgs + lane * 17;  // fg4_factor's scratch is idle here
-        rowsolve_lo(lo, DtA);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) my[c] = lo[c], XdT[c * kXS34 + lane] = lo[c] * disA[c];
-        rowsolve_hi(hi, my, DtA);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) XdT[(16 + c) * kXS34 + lane] = hi[c] * disA[16 + c];
-    } else if (warp == 1) {
-        invert_block(DtA, dabA, w->cminv + (size_t)(2 * k) * 1024, Scr, lane);
+        bar_grp(2);
     }
-    bar_grp(2);
-    // ---- block B, updated with the rows just solved: D' = D - X21 Sigma_A X21^T (lane = row, warp = column phase) ----
-#pragma unroll
-    for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = 4 * (warp + 4 * sl) + i;
-            a[sl][i] = (lane < jbB && c <= lane) ? A[(size_t)(k0 + 32 + c) * ld + k0 + 32 + lane] : (c == lane ? 1.0 : 0.0);
-        }
-    {
-        double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
-#pragma unroll 8
-        for (int kk = 0; kk < 32; ++kk) {
-            const double own = XdT[kk * kXS34 + lane] * sgA[kk];
-            const double2* cp0 = reinterpret_cast<const double2*>(XdT + kk * kXS34 + 4 * warp);
-            const double2* cp1 = reinterpret_cast<const double2*>(XdT + kk * kXS34 + 16 + 4 * warp);
-            const double2 c0a = cp0[0], c0b = cp0[1], c1a = cp1[0], c1b = cp1[1];
-            acc[0][0] = fma(own, c0a.x, acc[0][0]), acc[0][1] = fma(own, c0a.y, acc[0][1]);
-            acc[0][2] = fma(own, c0b.x, acc[0][2]), acc[0][3] = fma(own, c0b.y, acc[0][3]);
-            acc[1][0] = fma(own, c1a.x, acc[1][0]), acc[1][1] = fma(own, c1a.y, acc[1][1]);
-            acc[1][2] = fma(own, c1b.x, acc[1][2]), acc[1][3] = fma(own, c1b.y, acc[1][3]);
-        }
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[sl][i] -= acc[sl][i];
-    }
-    publish(fg4_factor(a, lane, warp, DtB, Fgs, 1), disB, dabB, sgB, 1);
-    bar_grp(2);
     // ---- the record for the panel kernel, the tile's own rows of the factor for the back substitution ----
 #pragma unroll
-    for (int i = 0; i < 8; ++i) rec[kRecDtA + tid + 128 * i] = DtA[tid + 128 * i], rec[kRecDtB + tid + 128 * i] = DtB[tid + 128 * i];
+    for (int i = 0; i < 8; ++i) rec[kRecDtA + tid + 128 * i] = Dt[0][tid + 128 * i], rec[kRecDtB + tid + 128 * i] = Dt[1][tid + 128 * i];
     for (int i = tid; i < 32 * kXS34; i += 128) rec[kRecX21 + i] = XdT[i];
     for (int i = tid; i < 6 * 32; i += 128) rec[kRecDisA + i] = Sc[i];
     if (tid < 2) rec[kRecNeg + tid] = (double)s_neg[tid];
-    if (tid < nb) w->cdinv[k0 + tid] = Sc[128 + tid];  // signs of this tile's pivots (update kernel)
+    if (tid < nb) w->cdinv[k0 + tid] = sg[tid];  // signs of this tile's pivots (update kernel)
     for (int i = tid; i < 32 * 32; i += 128) {  // Lf(k0 + 32 + r, k0 + c) = X21(r, c), row-major
         const int r = i >> 5, c = i & 31;
         if (r < jbB) w->Lfac[(size_t)(k0 + 32 + r) * ld + k0 + c] = XdT[c * kXS34 + r];
@@ -161,8 +143,8 @@ __global__ void __launch_bounds__(128) bigchol_diag_kernel(const DevWindow* __re
     if (tid == 0 && s_fail) w->lm->chol_fail = 1;
 }
 
-// rows [k0 + 64, n) of the panel and the rhs row: one thread per row, 64 rows per CTA; the last CTA of the grid inverts
-// block B of the diagonal tile instead (for the back substitution)
+// rows [k0 + 64, n) of the panel and the rhs row: one thread per row, 64 rows per CTA; the last CTA of the grid solves
+// the rows of the identity against block B instead (= its inverse, for the back substitution)
 constexpr int kPanelThreads = 64;
 __global__ void __launch_bounds__(kPanelThreads) bigchol_panel_kernel(const DevWindow* __restrict__ wp, int k) {
     const DevWindow* w = wp + blockIdx.y;
@@ -178,18 +160,15 @@ __global__ void __launch_bounds__(kPanelThreads) bigchol_panel_kernel(const DevW
     const int tid = threadIdx.x;
     for (int i = tid; i < kRecDoubles; i += kPanelThreads) Rec[i] = rec[i];
     __syncthreads();
-    const double* DtA = Rec + kRecDtA, *DtB = Rec + kRecDtB, *X21T = Rec + kRecX21;
-    const double* disA = Rec + kRecDisA, *disB = disA + 32, *dabB = disA + 96, *sgA = disA + 128;
-    if (blockIdx.x == gridDim.x - 1) {
-        if (tid < 32) invert_block(DtB, dabB, w->cminv + (size_t)(2 * k + 1) * 1024, Scr, tid);
-        return;
-    }
+    const double* X21T = Rec + kRecX21;
+    const double* dis = Rec + kRecDisA, *dab = dis + 64, *sg = dis + 128;  // [2][32] each (record layout: dis A, dis B, dab A, ...)
+    const bool inv = blockIdx.x == gridDim.x - 1;
     const int r = blockIdx.x * kPanelThreads + tid;
-    if (r >= rows) return;
-    const bool is_rhs = (r == rows - 1);
+    if (inv ? tid >= 32 : r >= rows) return;
+    const bool is_rhs = !inv && (r == rows - 1);
     double* const A = w->S;
     double* my = Scr + tid * 33;
-    auto src = [&](int c) { return is_rhs ? w->bs[k0 + c] : A[(size_t)(k0 + c) * ld + row0 + r]; };
+    auto src = [&](int c) { return c >= nb ? 0.0 : (is_rhs ? w->bs[k0 + c] : A[(size_t)(k0 + c) * ld + row0 + r]); };
     auto dst = [&](int c, double v) {
         if (c >= nb) return;
         if (is_rhs) {
@@ -199,58 +178,51 @@ __global__ void __launch_bounds__(kPanelThreads) bigchol_panel_kernel(const DevW
             w->Lfac[(size_t)(row0 + r) * ld + k0 + c] = v;  // row of the factor for the back substitution (row-major)
         }
     };
-    double lo[16], hi[16];
-    // ---- x1 = y1 M_A^-T Sigma_A ----
+    // half 0: x1 = y1 M_A^-T Sigma_A;  half 1: y2 -= (x1 Sigma_A) X21^T, x2 = y2 M_B^-T Sigma_B   (one copy of the solve)
+#pragma unroll 1
+    for (int half = inv ? 1 : 0; half < 2; ++half) {
+        if (half == 1 && nb <= 32) break;
+        const double* Dt = Rec + (half ? kRecDtB : kRecDtA);
+        double lo[16], hi[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) lo[c] = (c < nb) ? src(c) : 0.0, hi[c] = (16 + c < nb) ? src(16 + c) : 0.0;
-    rowsolve_lo(lo, DtA);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        my[c] = lo[c];
-        dst(c, lo[c] * disA[c]);
-    }
-    rowsolve_hi(hi, my, DtA);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const double v = hi[c] * disA[16 + c];
-        dst(16 + c, v);
-        my[16 + c] = v * sgA[16 + c];  // x1 Sigma_A for the product below
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) my[c] = my[c] * disA[c] * sgA[c];
-    if (nb <= 32) return;
-    // ---- y2 -= (x1 Sigma_A) X21^T, 16 columns at a time; x2 = y2 M_B^-T Sigma_B ----
-#pragma unroll
-    for (int c = 0; c < 16; ++c) lo[c] = (32 + c < nb) ? src(32 + c) : 0.0, hi[c] = (48 + c < nb) ? src(48 + c) : 0.0;
-#pragma unroll 4
-    for (int kk = 0; kk < 32; ++kk) {
-        const double xk = my[kk];
-        const double2* p = reinterpret_cast<const double2*>(X21T + kk * kXS34);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const double2 v = p[c];
-            lo[2 * c] = fma(-xk, v.x, lo[2 * c]), lo[2 * c + 1] = fma(-xk, v.y, lo[2 * c + 1]);
+        for (int c = 0; c < 16; ++c) {
+            lo[c] = inv ? (c == tid ? 1.0 : 0.0) : src(32 * half + c);
+            hi[c] = inv ? (16 + c == tid ? 1.0 : 0.0) : src(32 * half + 16 + c);
         }
-    }
-#pragma unroll 4
-    for (int kk = 0; kk < 32; ++kk) {
-        const double xk = my[kk];
-        const double2* p = reinterpret_cast<const double2*>(X21T + kk * kXS34 + 16);
+        if (half == 1 && !inv) {
+#pragma unroll 2
+            for (int kk = 0; kk < 32; ++kk) {
+                const double xk = my[kk];
+                const double2* p = reinterpret_cast<const double2*>(X21T + kk * kXS34);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const double2 v = p[c];
-            hi[2 * c] = fma(-xk, v.x, hi[2 * c]), hi[2 * c + 1] = fma(-xk, v.y, hi[2 * c + 1]);
+                for (int c = 0; c < 8; ++c) {
+                    const double2 v = p[c], u = p[8 + c];
+                    lo[2 * c] = fma(-xk, v.x, lo[2 * c]), lo[2 * c + 1] = fma(-xk, v.y, lo[2 * c + 1]);
+                    hi[2 * c] = fma(-xk, u.x, hi[2 * c]), hi[2 * c + 1] = fma(-xk, u.y, hi[2 * c + 1]);
+                }
+            }
         }
-    }
-    rowsolve_lo(lo, DtB);
+        const double* scale = (inv ? dab : dis) + 32 * half;
+        const double* sgh = sg + 32 * half;
+        double x1s[16];
+        rowsolve_lo(lo, Dt);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        my[c] = lo[c];
-        dst(32 + c, lo[c] * disB[c]);
-    }
-    rowsolve_hi(hi, my, DtB);
+        for (int c = 0; c < 16; ++c) {
+            my[c] = lo[c];
+            const double v = lo[c] * scale[c];
+            x1s[c] = v * sgh[c];
+            if (inv) w->cminv[(size_t)(2 * k + 1) * 1024 + c * 32 + tid] = v; else dst(32 * half + c, v);
+        }
+        rowsolve_hi(hi, my, Dt);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) dst(48 + c, hi[c] * disB[16 + c]);
+        for (int c = 0; c < 16; ++c) {
+            const double v = hi[c] * scale[16 + c];
+            if (inv) w->cminv[(size_t)(2 * k + 1) * 1024 + (16 + c) * 32 + tid] = v; else dst(32 * half + 16 + c, v);
+            my[16 + c] = v * sgh[16 + c];  // x1 Sigma_A for the product of the second half
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) my[c] = x1s[c];
+    }
 }
 
 // trailing tiles (I >= J > k): C_IJ -= P_I P_J^T ; diagonal tiles also b_J -= P_J y_k

@@ -200,14 +200,17 @@ __device__ __forceinline__ void backsub_blocks(int n, int ld, const double* __re
             s0 = fma(cur[i], (r < n) ? xs[r] : 0.0, s0);
             s1 = fma(cur[i + 1], (r + NW < n) ? xs[r + NW] : 0.0, s1);
         }
-        if (j0 + lane < n) {  // systems with more than 16 NW rows below a block: the rest straight from L2, 4 in flight
-            int r = j0 + NB + warp + NW * 16;
-            for (; r + 3 * NW < n; r += 4 * NW) {
-                const double l0 = __ldcg(Lf + (size_t)r * ld + j0 + lane), l1 = __ldcg(Lf + (size_t)(r + NW) * ld + j0 + lane);
-                const double l2 = __ldcg(Lf + (size_t)(r + 2 * NW) * ld + j0 + lane), l3 = __ldcg(Lf + (size_t)(r + 3 * NW) * ld + j0 + lane);
-                s0 = fma(l0, xs[r], s0), s1 = fma(l1, xs[r + NW], s1), s0 = fma(l2, xs[r + 2 * NW], s0), s1 = fma(l3, xs[r + 3 * NW], s1);
+        if (j0 + lane < n) {  // systems with more than 16 NW rows below a block: the rest straight from L2, 16 in flight
+            for (int r = j0 + NB + warp + NW * 16; r < n; r += 16 * NW) {
+                double l[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) l[i] = (r + i * NW < n) ? __ldcg(Lf + (size_t)(r + i * NW) * ld + j0 + lane) : 0.0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    s0 = fma(l[i], (r + i * NW < n) ? xs[r + i * NW] : 0.0, s0);
+                    s1 = fma(l[i + 1], (r + (i + 1) * NW < n) ? xs[r + (i + 1) * NW] : 0.0, s1);
+                }
             }
-            for (; r < n; r += NW) s0 = fma(__ldcg(Lf + (size_t)r * ld + j0 + lane), xs[r], s0);
         }
         part[warp * NB + lane] = s0 + s1;
         __syncthreads();
