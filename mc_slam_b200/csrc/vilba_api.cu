@@ -532,6 +532,17 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.max_trials = p.max_trials;
 }
 
+// Host threads one context may use for flatten / scatter.  Several processes share the host (one per GPU under torchrun:
+// LOCAL_WORLD_SIZE) and a split batch runs one thread per lane on top, so the budget is cores / (processes * lanes):
+// 8 processes x 4 lanes x 8 flatten threads on a 32-core host is what cost the 8-GPU end-to-end run 9 % in round 1.
+int host_thread_budget(int lanes) {
+    static const int fixed = std::getenv("VILBA_HOST_THREADS") ? std::max(1, std::atoi(std::getenv("VILBA_HOST_THREADS"))) : 0;
+    if (fixed) return fixed;
+    static const int procs = std::getenv("LOCAL_WORLD_SIZE") ? std::max(1, std::atoi(std::getenv("LOCAL_WORLD_SIZE"))) : 1;
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    return std::max(1, std::min(8, hw / (procs * std::max(1, lanes))));
+}
+
 template <class F>
 void parallel_for(int n, int max_threads, F&& f) {
     const int nt = std::max(1, std::min(n, max_threads));
@@ -606,7 +617,8 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     std::vector<WinMeta>& meta = ctx->meta;
     meta.assign(n_win, WinMeta());
     std::vector<int> status(n_win, VILBA_OK);
-    parallel_for(n_win, 8, [&](int i) {
+    const int host_threads = host_thread_budget(ctx->batch_total_hint > n_win ? ctx->n_lanes : 1);
+    parallel_for(n_win, host_threads, [&](int i) {
         const vilba_window* w = &wins[i];
         int st = check_window(w);
         if (st != VILBA_OK) {
@@ -681,7 +693,7 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     CK(ctx->pinned_small.reserve(sizeof(DevWindow) * (size_t)n_win + 256), "cudaMallocHost(desc)");
     char* h = ctx->pinned.base;
     char* d = ctx->arena.base;
-    parallel_for(n_win, 8, [&](int i) { pack_window(&wins[i], meta[i], h + meta[i].in_base); });
+    parallel_for(n_win, host_threads, [&](int i) { pack_window(&wins[i], meta[i], h + meta[i].in_base); });
     const auto t_packed = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(d, h, in_o, cudaMemcpyHostToDevice, ctx->stream), "H2D windows");
     if (std::getenv("VILBA_DEBUG_COUNTERS"))
@@ -905,7 +917,7 @@ int download_batch(vilba_ctx* ctx, vilba_result* out) {
     char* hp = ctx->pinned_out.base;
     CK(cudaMemcpyAsync(hp, ctx->arena.base + ctx->out_region, ctx->out_total, cudaMemcpyDeviceToHost, s), "D2H results");
     CK(cudaStreamSynchronize(s), "sync");
-    parallel_for(ctx->n_win, 8, [&](int i) {
+    parallel_for(ctx->n_win, host_thread_budget(ctx->batch_total_hint > ctx->n_win ? ctx->n_lanes : 1), [&](int i) {
         const WinMeta& m = ctx->meta[i];
         const char* src = hp + (m.out_base - ctx->out_region);
         vilba_result& o = out[i];
