@@ -465,12 +465,13 @@ def main():
             "workload": workload_desc(w4, "c4", 1) + f", map points sharded over {world} rank(s)",
             "lm_iters_per_sec": s_it / (s_ms_max * 1e-3), "ms_per_iter": s_ms_max / max(1, s_it), "ms_per_solve": s_ms_max / 3,
             "edges_per_rank": int(e1 - e0), "points_per_rank": int(p1 - p0),
-            "nccl_calls_per_slot": 4,
-            "allreduce_bytes_per_slot": int(8 * (n4 * n4 + n4) + 8 + 8 * (lds4 * n4 + n4) + 16),
+            "nccl_calls_per_slot": 3, "nccl_calls_per_trial": 2,
+            "allreduce_bytes_per_slot": int(8 * (n4 + world) + 8 * (lds4 * n4 + n4) + 16),
             "chol_ms": sp.solve_ms / max(1, sp.solve_launches), "schur_ms": sp.schur_ms / max(1, sp.schur_launches),
             "linearize_ms": sp.linearize_ms / max(1, sp.linearize_launches),
-            "note": "one slot = linearise-if-needed + one LM trial; allreduce(sum) of H_pp|b_p and of S|b_s, allreduce(max) of "
-                    "max diag H_ll, allreduce(sum) of chi2|scale; the reduced system is solved redundantly on every rank; "
+            "note": "one slot = linearise-if-needed + one LM trial; per trial allreduce(sum) of S|b_s and of chi2|scale, per "
+                    "linearisation allreduce(sum) of [diag H_pp | per-rank max diag H_ll] (H_pp and b_p stay rank-local: every "
+                    "rank folds its partial sums into its partial S); the reduced system is solved redundantly on every rank; "
                     "device time (CUDA events), max over ranks, 3 solves after 1 warm-up; per-kernel times from a profiled solve"}
         cs.close()
 

@@ -96,7 +96,11 @@ struct DevWindow {
     double* bp_w;
     double* S_w;
     double* bs_w;
-    int shard_owner;  // 1: this rank adds the terms that exist once per window (IMU edges, H_pp + lambda I in S); whole window: 1
+    int shard_owner;  // 1: this rank adds the terms that exist once per window (IMU edges, lambda I in S); whole window: 1
+    int sharded;      // 1: point-sharded over several GPUs: Hpp / bp hold THIS RANK's partial sums (they never cross the wire:
+                      // every rank folds its own partial H_pp into its partial S), diag_red carries what lambda's start needs
+    int shard_rank, shard_world;
+    double* diag_red; // n + shard_world: diag(H_pp) (summed over the ranks) | max |diag H_ll| of every rank
     double* Hll;  // P * 6   (xx,xy,xz,yy,yz,zz)
     double* bl;   // P * 3
     double* W;    // E * 18  H_pl block of the edge, 6x3 rows [P,Phi]
@@ -168,7 +172,7 @@ cudaError_t launch_preint_batch(cudaStream_t stream, int n_pairs, const int* sam
                                 double* out, double gyr_cov, double acc_cov, int group);
 
 // point-sharded window: collectives the host controller inserts between the kernels of a slot
-enum SlotReduce { RED_HPP = 0, RED_MAXDIAG = 1, RED_S = 2, RED_CHI = 3 };
+enum SlotReduce { RED_DIAG = 0, RED_S = 2, RED_CHI = 3 };
 struct SlotComm {
     void* self;
     cudaError_t (*reduce)(void* self, int which, cudaStream_t s);

@@ -248,14 +248,18 @@ __global__ void __launch_bounds__(256) lm_iter_begin_kernel(const DevWindow* __r
     __shared__ double red[8];
     const int iteration = s->iter;
     double m = 0.0;
-    if (iteration == 0)
-        for (int d = threadIdx.x; d < w.n; d += blockDim.x) m = fmax(m, fabs(w.Hpp[(size_t)d * w.n + d]));
+    if (iteration == 0) {
+        if (w.sharded)  // diag(H_pp) summed over the ranks | every rank's max |diag H_ll| (RED_DIAG)
+            for (int d = threadIdx.x; d < w.n + w.shard_world; d += blockDim.x) m = fmax(m, fabs(w.diag_red[d]));
+        else
+            for (int d = threadIdx.x; d < w.n; d += blockDim.x) m = fmax(m, fabs(w.Hpp[(size_t)d * w.n + d]));
+    }
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         if (iteration == 0) {  // computeLambdaInit (optimization_algorithm_levenberg.cpp:166-180)
-            double mx = __longlong_as_double((long long)s->maxdiag_bits);
+            double mx = w.sharded ? 0.0 : __longlong_as_double((long long)s->maxdiag_bits);
             for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, red[i]);
             s->lambda = w.lm_tau * mx;
             s->ni = 2.0;
@@ -278,7 +282,8 @@ __global__ void __launch_bounds__(32) lm_decide_kernel(const DevWindow* __restri
     if (s->phase != PH_TRIAL) return;
     const double lambda = s->lambda;
     double sc = 0.0;  // computeScale over the pose part (:182-189); landmarks arrive in scale_acc
-    for (int j = threadIdx.x; j < w.n; j += 32) sc += w.x[j] * (lambda * w.x[j] + w.bp[j]);
+    if (!w.sharded)   // (sharded: shard_scale_kernel added it to scale_acc before the reduction, b_p is a partial sum here)
+        for (int j = threadIdx.x; j < w.n; j += 32) sc += w.x[j] * (lambda * w.x[j] + w.bp[j]);
     sc = warp_sum(sc);
     if (threadIdx.x == 0) {
         double scale = sc + s->scale_acc;
@@ -330,6 +335,29 @@ __global__ void __launch_bounds__(32) lm_decide_kernel(const DevWindow* __restri
             s->phase = (res != 0 || s->iter >= s->max_iters || s->stop) ? PH_DONE : PH_LINEARIZE;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// point-sharded window: the two small pieces that replace the allreduce of H_pp | b_p
+// ------------------------------------------------------------------------------------------------
+// after assemble_hpp: diag(H_pp) of this rank's partial sum and its max |diag H_ll| into the buffer RED_DIAG sums
+__global__ void __launch_bounds__(256) shard_diag_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow* w = wp + blockIdx.y;
+    if (!w->sharded) return;
+    const bool lin = w->lm->phase == PH_LINEARIZE;  // other phases: zeros (the in-place sum behind this kernel runs in every slot)
+    for (int d = threadIdx.x; d < w->n + w->shard_world; d += blockDim.x)
+        w->diag_red[d] = !lin ? 0.0 : d < w->n ? w->Hpp[(size_t)d * w->n + d]
+                                  : (d - w->n == w->shard_rank ? __longlong_as_double((long long)w->lm->maxdiag_bits) : 0.0);
+}
+// after update_eval: the pose part of computeScale from this rank's partial b_p (lambda x^2 once per window)
+__global__ void __launch_bounds__(32) shard_scale_kernel(const DevWindow* __restrict__ wp) {
+    const DevWindow* w = wp + blockIdx.y;
+    if (w->lm->phase != PH_TRIAL || !w->sharded) return;
+    const double lambda = w->shard_owner ? w->lm->lambda : 0.0;
+    double sc = 0.0;
+    for (int j = threadIdx.x; j < w->n; j += 32) sc += w->x[j] * (lambda * w->x[j] + w->bp[j]);
+    sc = warp_sum(sc);
+    if (threadIdx.x == 0) w->lm->scale_acc += sc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,6 +456,14 @@ cudaError_t launch_stage_begin(cudaStream_t s, const DevWindow* wp, const Launch
 }
 cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
     lm_iter_begin_kernel<<<dim3(1, d.n_windows), 256, 0, s>>>(wp);
+    return cudaGetLastError();
+}
+cudaError_t launch_shard_diag(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    shard_diag_kernel<<<dim3(1, d.n_windows), 256, 0, s>>>(wp);
+    return cudaGetLastError();
+}
+cudaError_t launch_shard_scale(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {
+    shard_scale_kernel<<<dim3(1, d.n_windows), 32, 0, s>>>(wp);
     return cudaGetLastError();
 }
 cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp, const LaunchDims& d) {

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWi
         const int rr = i / 15, c = i - 15 * rr;
         const int gr = 15 * a + rr, gc = 15 * b + c;
         if (gr > gc) continue;
-        double v = w.shard_owner ? w.Hpp[(size_t)gr * n + gc] : 0.0;
+        double v = w.Hpp[(size_t)gr * n + gc];  // (a sharded rank: its own partial sum)
         if (gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
         const int pr = pose6_index(rr), pc = pose6_index(c);
         if (pr >= 0 && pc >= 0) v -= blockacc[6 * pr + pc];
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kSchurThreads) schur_gather_kernel(const DevWi
     }
     if (diag && threadIdx.x < 15) {
         const int rr = threadIdx.x;
-        double v = w.shard_owner ? w.bp[15 * a + rr] : 0.0;
+        double v = w.bp[15 * a + rr];
         const int pr = pose6_index(rr);
         if (pr >= 0) v -= blockacc[36 + pr];
         w.bs_w[15 * a + rr] = v;
@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(256) schur_finish_pair_kernel(const DevWindow*
         }
         const int a = gr / 15, b = gc / 15, rr = gr - 15 * a, cc = gc - 15 * b;
         const int pr = pose6_index(rr), pc = pose6_index(cc);
-        double v = !w.shard_owner ? 0.0 : (is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc]);
+        double v = is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc];  // (a sharded rank: its own partial sums)
         if (!is_rhs && gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
         if (pr >= 0 && (is_rhs || pc >= 0)) {
             const int R = ts_replicas(b - a, nf);
@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __re
         }
         const int a = gr / 15, b = gc / 15, rr = gr - 15 * a, cc = gc - 15 * b;
         const int pr = pose6_index(rr), pc = pose6_index(cc);
-        double v = !w.shard_owner ? 0.0 : (is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc]);
+        double v = is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc];  // (a sharded rank: its own partial sums)
         if (!is_rhs && gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
         if (pr >= 0 && (is_rhs || pc >= 0)) {
             const size_t off = is_rhs ? (size_t)(nf * (nf + 1) / 2) * 36 + 6 * a + pr
@@ -999,6 +999,8 @@ size_t linearize_smem_bytes(int K, int n_free) { return linearize_v2_smem_bytes(
 cudaError_t launch_update_eval_apply(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_shard_diag(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
+cudaError_t launch_shard_scale(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t configure_point_kernels(const LaunchDims& d);
 cudaError_t configure_chol(const LaunchDims& d);
@@ -1031,9 +1033,9 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     reduce_partials_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.point_grid);
     if ((e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) return e;
     assemble_hpp_kernel<<<dim3(d.assemble_grid, d.n_windows), 256, 0, s>>>(wp);
-    if (comm) {  // sharded window: H_pp | b_p = sum over ranks, max |diag H_ll| = max over ranks
-        if ((e = comm->reduce(comm->self, RED_HPP, s)) != cudaSuccess) return e;
-        if ((e = comm->reduce(comm->self, RED_MAXDIAG, s)) != cudaSuccess) return e;
+    if (comm) {  // sharded window: only what computeLambdaInit needs crosses the wire (diag H_pp summed, max |diag H_ll|)
+        if ((e = launch_shard_diag(s, wp, d)) != cudaSuccess) return e;
+        if ((e = comm->reduce(comm->self, RED_DIAG, s)) != cudaSuccess) return e;
     }
     if (probe && (e = cudaEventRecord(probe[1], s)) != cudaSuccess) return e;
     if ((e = launch_lm_iter_begin(s, wp, d)) != cudaSuccess) return e;
@@ -1063,7 +1065,10 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     if (e != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;
     if ((e = launch_update_eval_apply(s, wp, d)) != cudaSuccess) return e;
-    if (comm && (e = comm->reduce(comm->self, RED_CHI, s)) != cudaSuccess) return e;  // chi2 and the landmark part of the gain scale
+    if (comm) {  // chi2 and the gain scale: landmark part from update_eval, pose part from this rank's partial b_p
+        if ((e = launch_shard_scale(s, wp, d)) != cudaSuccess) return e;
+        if ((e = comm->reduce(comm->self, RED_CHI, s)) != cudaSuccess) return e;
+    }
     if (probe && (e = cudaEventRecord(probe[5], s)) != cudaSuccess) return e;
     if ((e = launch_lm_decide(s, wp, d)) != cudaSuccess) return e;
     return cudaGetLastError();

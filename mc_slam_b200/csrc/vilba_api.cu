@@ -80,7 +80,7 @@ struct Layout {
     // work region; offsets relative to wk_base
     size_t edge_pt, pair_begin, pair_ea, pair_eb, pt_mask;
     size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y,
-        schur_partial, ts_rec, ts_hdr, S, Lfac, cminv, cdinv, bs, x, dbg, outlier, chi_partial, chi_counter, Hpp_part, S_part, hpp_span, s_span, wk_bytes;
+        schur_partial, ts_rec, ts_hdr, S, Lfac, cminv, cdinv, bs, x, dbg, outlier, chi_partial, chi_counter, diag_red, S_part, hpp_span, s_span, wk_bytes;
 };
 
 struct WinMeta {
@@ -158,8 +158,8 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bo
     L.outlier = take(E);
     L.chi_partial = take(sizeof(double) * 2 * (size_t)lin_ctas);
     L.chi_counter = take(sizeof(unsigned) * 4);
-    L.Hpp_part = take(sharded ? L.hpp_span : 0);  // send buffers of the two allreduces
-    L.S_part = take(sharded ? L.s_span : 0);
+    L.diag_red = take(sharded ? sizeof(double) * (n + 64) : 0);  // diag(H_pp) | per-rank max |diag H_ll| (one small allreduce)
+    L.S_part = take(sharded ? L.s_span : 0);                     // send buffer of the allreduce of S | b_s
     L.wk_bytes = o;
     return L;
 }
@@ -474,9 +474,12 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.Hpp = reinterpret_cast<double*>(wk + L.Hpp);
     dw.bp = reinterpret_cast<double*>(wk + L.bp);
     const bool sharded = ctx->comm != nullptr;
-    dw.Hpp_w = sharded ? reinterpret_cast<double*>(wk + L.Hpp_part) : dw.Hpp;
-    dw.bp_w = sharded ? reinterpret_cast<double*>(wk + L.Hpp_part + (L.bp - L.Hpp)) : dw.bp;
+    dw.Hpp_w = dw.Hpp;  // (sharded: this rank's partial sums stay on this rank)
+    dw.bp_w = dw.bp;
     dw.shard_owner = (!sharded || ctx->comm_rank == 0) ? 1 : 0;
+    dw.sharded = sharded ? 1 : 0;
+    dw.shard_rank = ctx->comm_rank, dw.shard_world = ctx->comm_world;
+    dw.diag_red = reinterpret_cast<double*>(wk + L.diag_red);
     dw.Hll = reinterpret_cast<double*>(wk + L.Hll);
     dw.bl = reinterpret_cast<double*>(wk + L.bl);
     dw.W = reinterpret_cast<double*>(wk + L.W);
@@ -559,9 +562,12 @@ void parallel_for(int n, int max_threads, F&& f) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// point-sharded window: the three exchanges of one LM slot, all on the library stream.
-// Every reduction goes from a send buffer that only this rank's kernels write into the buffer the next
-// kernel reads, so repeating it in a slot whose phase does not need it is harmless.
+// point-sharded window: the three exchanges of one LM slot, all on the library stream: a small one after
+// the linearisation (what computeLambdaInit needs), S | b_s after the Schur step, chi2 | scale after the update.  H_pp
+// and b_p never cross the wire: every rank folds its own partial sums into its partial S.  The reductions are enqueued
+// unconditionally (the device-side controller skips the kernels); S | b_s goes from a send buffer only this rank's
+// kernels write, the two small ones are in place behind kernels that rewrite their inputs only in the phase that
+// uses them, so repeating them in a slot whose phase does not need them is harmless.
 // ------------------------------------------------------------------------------------------------
 void* open_nccl() {
     static void* lib = nullptr;
@@ -576,11 +582,8 @@ cudaError_t slot_reduce(void* self, int which, cudaStream_t s) {
     const Layout& L = ctx->meta[0].L;
     ncclResult_t r = ncclSuccess;
     switch (which) {
-        case RED_HPP:
-            r = ctx->p_ncclAllReduce(dw.Hpp_w, dw.Hpp, L.hpp_span / sizeof(double), ncclDouble, ncclSum, ctx->comm, s);
-            break;
-        case RED_MAXDIAG:  // bits of non-negative doubles order like the values
-            r = ctx->p_ncclAllReduce(&dw.lm->maxdiag_bits, &dw.lm->maxdiag_bits, 1, ncclUint64, ncclMax, ctx->comm, s);
+        case RED_DIAG:  // diag(H_pp) summed | every rank's max |diag H_ll| in its own slot (zeros elsewhere): one sum
+            r = ctx->p_ncclAllReduce(dw.diag_red, dw.diag_red, (size_t)dw.n + (size_t)ctx->comm_world, ncclDouble, ncclSum, ctx->comm, s);
             break;
         case RED_S:
             r = ctx->p_ncclAllReduce(dw.S_w, dw.S, L.s_span / sizeof(double), ncclDouble, ncclSum, ctx->comm, s);
@@ -1197,7 +1200,7 @@ int vilba_comm_unique_id(void* out128) {
 }
 
 int vilba_comm_init(vilba_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world) {
-    if (!ctx || !unique_id128 || world < 1 || rank < 0 || rank >= world || ctx->comm) return VILBA_ERR_ARG;
+    if (!ctx || !unique_id128 || world < 1 || world > 64 || rank < 0 || rank >= world || ctx->comm) return VILBA_ERR_ARG;
     void* lib = open_nccl();
     if (!lib) {
         ctx->err = "libnccl.so.2 not found";
