@@ -59,6 +59,13 @@ extern "C" {
 #define VILBA_KF_FIXED 1u      /* VertexNavStatePVR::setFixed(true)   (src/Optimizer.cpp:2454-2467)        */
 #define VILBA_KF_HAS_BIAS 2u   /* a VertexNavStateBias exists for it  (src/Optimizer.cpp:2435-2443,2470-2478) */
 
+/* vilba_params.mode: which caller's optimisation schedule the solve follows */
+#define VILBA_MODE_SINGLE_STAGE 1u    /* one optimize(iters_stage1): no cull, no second stage, the stop flag does
+                                         not abort before the solve (GlobalBundleAdjustmentNavState,
+                                         src/Optimizer.cpp:1621-1624)                                            */
+#define VILBA_MODE_MONO_NOT_ROBUST 2u /* mono edges are built without a Huber kernel (bRobust == false,
+                                         src/Optimizer.cpp:1590-1595)                                            */
+
 /* status codes */
 #define VILBA_OK 0
 #define VILBA_ABORTED 1          /* *stop_flag was set before optimisation: nothing written (Optimizer.cpp:2643-2645) */
@@ -74,7 +81,7 @@ typedef struct vilba_params {
     int32_t iters_stage1;      /* 5   optimizer.optimize(5)   src/Optimizer.cpp:2648                   */
     int32_t iters_stage2;      /* 10  optimizer.optimize(10)  src/Optimizer.cpp:2676                   */
     int32_t max_trials;        /* 10  _maxTrialsAfterFailure  optimization_algorithm_levenberg.cpp:51  */
-    int32_t reserved0;
+    int32_t mode;              /* VILBA_MODE_* flags; 0 = LocalBundleAdjustmentNavState                   */
     double huber_mono;         /* (double)(float)sqrt(5.991)        Optimizer.cpp:2580,2624            */
     double huber_pvr;          /* (double)(float)sqrt(100*21.666)   Optimizer.cpp:2487                 */
     double huber_bias;         /* (double)(float)sqrt(100*16.812)   Optimizer.cpp:2488                 */
@@ -180,6 +187,23 @@ const char* vilba_version(void);
  * ------------------------------------------------------------------------------------------- */
 int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out,
                    const volatile uint8_t* stop_flag);
+
+/* ---------------------------------------------------------------------------------------------
+ * Entry 1b: global BA.  Replaces the optimisation of Optimizer::GlobalBundleAdjustmentNavState
+ * (src/Optimizer.cpp:1392-1668): the same vertices and edges as the local BA, built over
+ * the whole map (`win` = every good key-frame, the one with mnId 0 flagged VILBA_KF_FIXED | VILBA_KF_HAS_BIAS, and
+ * every map point with at least one observation), then ONE optimize(n_iterations) -- no cull, no second stage.
+ * `robust` is the reference's `bRobust`: when non-zero every edge carries a Huber kernel with the thresholds of
+ * Optimizer.cpp:1438-1439,1541 (sqrt(21.666), sqrt(16.812), sqrt(5.99), each rounded to float); when zero no edge
+ * has one.  The context's own parameters are used for everything else and are left unchanged.
+ * A stop flag that is already set makes g2o run zero iterations (sparse_optimizer.cpp:376): the call returns
+ * VILBA_OK with the input estimates, as the reference writes them back.  out->obs_outlier / obs_chi2 are filled
+ * from the final errors with the context's chi2 gate; the reference does not read them on this path.
+ * ------------------------------------------------------------------------------------------- */
+int vilba_global_ba(vilba_ctx* ctx, const vilba_window* win, int32_t n_iterations, int32_t robust, vilba_result* out,
+                    const volatile uint8_t* stop_flag);
+/* the parameters vilba_global_ba solves with, derived from `base` (NULL = defaults) */
+void vilba_global_ba_params(const vilba_params* base, int32_t n_iterations, int32_t robust, vilba_params* p);
 
 /* Many independent windows in one call (BASELINE config 5).  The windows are solved in batched launches
  * (a few concurrent lanes of up to vilba_max_batch() windows each); out[i] corresponds to win[i]. */

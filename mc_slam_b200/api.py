@@ -63,6 +63,18 @@ class Context:
         self._check(st, "vilba_local_ba")
         return res.take(cr)
 
+    # ---- entry 1b: Optimizer::GlobalBundleAdjustmentNavState (src/Optimizer.cpp:1392-1668) -------
+    def global_ba(self, win: Window, n_iterations: int = 10, robust: bool = False,
+                  stop_flag: Optional[np.ndarray] = None) -> Result:
+        """`win` is the whole map as one window: every good key-frame (mnId 0 fixed, all with a bias vertex) and
+        every map point with an observation; one optimize(n_iterations), no cull."""
+        res = Result.alloc(win)
+        cw, cr = win.as_c(), res.as_c()
+        sf = stop_flag.ctypes.data_as(C.POINTER(C.c_uint8)) if stop_flag is not None else None
+        st = self._lib.vilba_global_ba(self._h, C.byref(cw), int(n_iterations), int(bool(robust)), C.byref(cr), sf)
+        self._check(st, "vilba_global_ba")
+        return res.take(cr)
+
     def local_ba_batch(self, wins: Sequence[Window]) -> List[Result]:
         n = len(wins)
         results = [Result.alloc(w) for w in wins]

@@ -34,7 +34,7 @@ class Params(C.Structure):
         ("iters_stage1", C.c_int32),
         ("iters_stage2", C.c_int32),
         ("max_trials", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("mode", C.c_int32),
         ("huber_mono", C.c_double),
         ("huber_pvr", C.c_double),
         ("huber_bias", C.c_double),
@@ -47,6 +47,27 @@ class Params(C.Structure):
         ("gyr_meas_cov", C.c_double),
         ("acc_meas_cov", C.c_double),
     ]
+
+
+MODE_SINGLE_STAGE = 1  # VILBA_MODE_SINGLE_STAGE
+MODE_MONO_NOT_ROBUST = 2  # VILBA_MODE_MONO_NOT_ROBUST
+
+
+def global_ba_params(n_iterations: int, robust: bool, base: Optional["Params"] = None) -> "Params":
+    """Host-side restatement of vilba_global_ba_params: the settings of Optimizer::GlobalBundleAdjustmentNavState
+    (src/Optimizer.cpp:1438-1439,1541,1590-1595,1624).  The tests hand these to the oracle."""
+    p = Params()
+    C.memmove(C.byref(p), C.byref(base if base is not None else default_params()), C.sizeof(Params))
+    p.mode = MODE_SINGLE_STAGE | (0 if robust else MODE_MONO_NOT_ROBUST)
+    p.iters_stage1 = int(n_iterations)
+    p.iters_stage2 = 0
+    if robust:
+        p.huber_pvr = float(np.float32(np.sqrt(21.666)))
+        p.huber_bias = float(np.float32(np.sqrt(16.812)))
+        p.huber_mono = float(np.float32(np.sqrt(5.99)))
+    else:
+        p.huber_pvr = p.huber_bias = float("inf")
+    return p
 
 
 def default_params() -> Params:
@@ -343,6 +364,8 @@ EXPORTED_SYMBOLS = [  # every symbol include/vilba.h declares
     "vilba_last_error",
     "vilba_version",
     "vilba_local_ba",
+    "vilba_global_ba",
+    "vilba_global_ba_params",
     "vilba_local_ba_batch",
     "vilba_window_upload",
     "vilba_window_solve_resident",
@@ -396,6 +419,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vilba_version.restype = C.c_char_p
     lib.vilba_local_ba.argtypes = [C.c_void_p, C.POINTER(CWindow), C.POINTER(CResult), _c_uint8_p]
     lib.vilba_local_ba.restype = C.c_int
+    lib.vilba_global_ba.argtypes = [C.c_void_p, C.POINTER(CWindow), C.c_int32, C.c_int32, C.POINTER(CResult), _c_uint8_p]
+    lib.vilba_global_ba.restype = C.c_int
+    lib.vilba_global_ba_params.argtypes = [C.POINTER(Params), C.c_int32, C.c_int32, C.POINTER(Params)]
+    lib.vilba_global_ba_params.restype = None
     lib.vilba_local_ba_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CWindow), C.POINTER(CResult)]
     lib.vilba_local_ba_batch.restype = C.c_int
     lib.vilba_window_upload.argtypes = [C.c_void_p, C.POINTER(CWindow)]

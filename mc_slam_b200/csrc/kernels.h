@@ -201,11 +201,12 @@ struct LaunchDims {
     int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
     size_t smem_point;    // dynamic shared memory of update_eval / flags
     size_t smem_lin;      // ... of linearize_v2
+    int lin_threads;      // threads per CTA of linearize_v2: fewer warps (= fewer private accumulators) for many free key-frames
     size_t smem_chol;     // ... of chol_cluster
     size_t smem_sp;       // ... of schur_tile
 };
 size_t point_smem_bytes(int K);
-size_t linearize_smem_bytes(int K, int n_free);
+size_t linearize_smem_bytes(int K, int n_free, int threads);
 size_t chol_smem_bytes(int n);
 bool schur_tile_fits(int K, int n_free);   // the tile-scan Schur kernel handles windows of <= 32 key-frames
 size_t schur_tile_smem_bytes(int max_K, int tile_pts);

@@ -994,7 +994,7 @@ __global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __re
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-size_t linearize_smem_bytes(int K, int n_free) { return linearize_v2_smem_bytes(K, n_free, kPointThreads / 32); }
+size_t linearize_smem_bytes(int K, int n_free, int threads) { return linearize_v2_smem_bytes(K, n_free, threads / 32); }
 
 cudaError_t launch_update_eval_apply(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
@@ -1028,7 +1028,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
     linearize_imu_v2_kernel<<<dim3(d.imu_grid, d.n_windows), 32, 0, side>>>(wp);
     if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
-    linearize_v2_kernel<<<dim3(d.point_grid, d.n_windows), kPointThreads, d.smem_lin, s>>>(wp);
+    linearize_v2_kernel<<<dim3(d.point_grid, d.n_windows), d.lin_threads, d.smem_lin, s>>>(wp);
     if (probe && (e = cudaEventRecord(probe[7], s)) != cudaSuccess) return e;
     reduce_partials_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.point_grid);
     if ((e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) return e;

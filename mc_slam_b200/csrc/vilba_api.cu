@@ -337,6 +337,14 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
     d.gather_grid = std::max(2, 2 * sm / n_win);
     d.reduce_grid = std::max(2, sm / n_win);
     d.assemble_grid = std::max(4, 8 * sm / n_win);
+    // linearize_v2 keeps one private [P,Phi] accumulator per warp and free key-frame in shared memory: windows with
+    // many free key-frames (a global BA) run it with fewer warps per CTA.  Sized by the current batch.
+    {
+        const int K32 = std::max(32, (max_K + 31) / 32 * 32), nf8 = std::max(8, (max_nf + 7) / 8 * 8);
+        d.lin_threads = kPointThreads;
+        while (d.lin_threads > 32 && linearize_smem_bytes(K32, nf8, d.lin_threads) > 227 * 1024) d.lin_threads /= 2;
+        d.smem_lin = linearize_smem_bytes(K32, nf8, d.lin_threads);
+    }
     // tile-scan Schur kernel for windows of <= 32 key-frames, else the gather over pair lists
     d.sp_warps = d.sp_sets = d.sp_grid = d.sp_tile_pts = 0;
     d.smem_sp = 0;
@@ -397,7 +405,7 @@ void drop_graphs(vilba_ctx* ctx) {
 
 // flatten one window into its slice of the pinned staging buffer (phase A/B of the reference function:
 // gather + graph build, Optimizer.cpp:2329-2639, become "pack + one H2D")
-void pack_window(const vilba_window* w, const WinMeta& m, char* h) {
+void pack_window(const vilba_window* w, const WinMeta& m, char* h, int mono_flags) {
     const Layout& L = m.L;
     const int K = m.K, NI = m.NI, P = m.P, E = m.E, n_free = m.n_free, n_pairs = m.n_pairs;
     std::memcpy(h + L.kf_state0, w->kf_state, sizeof(double) * 22 * (size_t)K);
@@ -409,7 +417,7 @@ void pack_window(const vilba_window* w, const WinMeta& m, char* h) {
         std::memcpy(&r.x, &w->obs_uv[2 * (size_t)e], 4);
         std::memcpy(&r.y, &w->obs_uv[2 * (size_t)e + 1], 4);
         std::memcpy(&r.z, &w->obs_inv_sigma2[e], 4);
-        r.w = w->obs_kf[e] | OBS_ROBUST;  // every mono edge starts with its Huber kernel (Optimizer.cpp:2622-2624)
+        r.w = w->obs_kf[e] | mono_flags;  // OBS_ROBUST: the edge starts with its Huber kernel (Optimizer.cpp:2622-2624)
         ho[e] = r;
     }
     if (P) std::memcpy(h + L.pt_obs_begin, w->pt_obs_begin, sizeof(int) * ((size_t)P + 1));
@@ -665,11 +673,6 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
         ctx->cap_nf = std::max(ctx->cap_nf, (max_nf + 7) / 8 * 8);
         ctx->cap_n = std::max(ctx->cap_n, 15 * ctx->cap_nf);
         ctx->dims.smem_point = point_smem_bytes(ctx->cap_K);
-        ctx->dims.smem_lin = linearize_smem_bytes(ctx->cap_K, ctx->cap_nf);
-        if (ctx->dims.smem_lin > 227 * 1024) {
-            ctx->err = "window too large for the shared-memory stages";
-            return VILBA_ERR_ARG;
-        }
         ctx->dims.chol_cluster = ctx->chol_cluster;
         CK(configure_kernels(ctx->dims), "cudaFuncSetAttribute");
         drop_graphs(ctx);
@@ -696,7 +699,8 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     CK(ctx->pinned_small.reserve(sizeof(DevWindow) * (size_t)n_win + 256), "cudaMallocHost(desc)");
     char* h = ctx->pinned.base;
     char* d = ctx->arena.base;
-    parallel_for(n_win, host_threads, [&](int i) { pack_window(&wins[i], meta[i], h + meta[i].in_base); });
+    const int mono_flags = (ctx->prm.mode & VILBA_MODE_MONO_NOT_ROBUST) ? 0 : OBS_ROBUST;
+    parallel_for(n_win, host_threads, [&](int i) { pack_window(&wins[i], meta[i], h + meta[i].in_base, mono_flags); });
     const auto t_packed = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(d, h, in_o, cudaMemcpyHostToDevice, ctx->stream), "H2D windows");
     if (std::getenv("VILBA_DEBUG_COUNTERS"))
@@ -753,7 +757,7 @@ bool same_dims(const LaunchDims& a, const LaunchDims& b) {
            a.gather_grid == b.gather_grid && a.reduce_grid == b.reduce_grid && a.assemble_grid == b.assemble_grid &&
            a.sp_warps == b.sp_warps && a.sp_sets == b.sp_sets && a.sp_grid == b.sp_grid && a.sp_tile_pts == b.sp_tile_pts &&
            a.sp_pair_lanes == b.sp_pair_lanes && a.chol_cluster == b.chol_cluster && a.chol_big_tiles == b.chol_big_tiles &&
-           a.chol_nb == b.chol_nb && a.chol_la == b.chol_la && a.chol_n == b.chol_n && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.smem_chol == b.smem_chol &&
+           a.chol_nb == b.chol_nb && a.chol_la == b.chol_la && a.chol_n == b.chol_n && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.lin_threads == b.lin_threads && a.smem_chol == b.smem_chol &&
            a.smem_sp == b.smem_sp;
 }
 
@@ -870,7 +874,10 @@ int solve_batch(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_
         out[i].solve_ms = 0.0;
         out[i].status = VILBA_OK;
     }
-    if (stop_requested(stop_flag)) {  // Optimizer.cpp:2643-2645
+    // VILBA_MODE_SINGLE_STAGE (GlobalBundleAdjustmentNavState): one optimize(), which g2o ends after zero iterations
+    // when the flag is already up (sparse_optimizer.cpp:376), and the estimates are written back all the same
+    const bool single_stage = (ctx->prm.mode & VILBA_MODE_SINGLE_STAGE) != 0;
+    if (!single_stage && stop_requested(stop_flag)) {  // Optimizer.cpp:2643-2645
         for (int i = 0; i < nw; ++i) out[i].status = VILBA_ABORTED;
         return VILBA_ABORTED;
     }
@@ -884,11 +891,12 @@ int solve_batch(vilba_ctx* ctx, vilba_result* out, const volatile uint8_t* stop_
     ctx->stats.kernel_launches += 2;
     std::vector<LmState> lm(nw);
     std::memset(lm.data(), 0, sizeof(LmState) * (size_t)nw);
-    int r = run_stage(ctx, 1, ctx->prm.iters_stage1, out, stop_flag, lm);
+    int r = VILBA_OK;
+    if (!stop_requested(stop_flag) && ctx->prm.iters_stage1 > 0) r = run_stage(ctx, 1, ctx->prm.iters_stage1, out, stop_flag, lm);
     if (r != VILBA_OK) return r;
     bool stopped = stop_requested(stop_flag);
     for (int i = 0; i < nw; ++i) stopped = stopped || lm[i].stop;
-    if (!stopped) {  // bDoMore (Optimizer.cpp:2650-2656)
+    if (!stopped && !single_stage) {  // bDoMore (Optimizer.cpp:2650-2656)
         CK(launch_cull(s, ctx->dwp, ctx->dims), "cull");
         ctx->stats.kernel_launches += 1;
         r = run_stage(ctx, 2, ctx->prm.iters_stage2, out, stop_flag, lm);
@@ -1266,6 +1274,46 @@ int vilba_local_ba(vilba_ctx* ctx, const vilba_window* win, vilba_result* out, c
     int r = upload_batch(ctx, 1, win);
     if (r == VILBA_OK) r = solve_batch(ctx, out, stop_flag);
     if (r == VILBA_OK) r = download_batch(ctx, out);
+    out->status = r;
+    return r;
+}
+
+void vilba_global_ba_params(const vilba_params* base, int32_t n_iterations, int32_t robust, vilba_params* p) {
+    if (base) *p = *base;
+    else vilba_default_params(p);
+    p->mode = VILBA_MODE_SINGLE_STAGE | (robust ? 0 : VILBA_MODE_MONO_NOT_ROBUST);
+    p->iters_stage1 = n_iterations;  // optimizer.optimize(nIterations)  Optimizer.cpp:1624
+    p->iters_stage2 = 0;
+    if (robust) {
+        p->huber_pvr = (double)(float)std::sqrt(21.666);   // const float thHuberNavStatePVR   Optimizer.cpp:1438
+        p->huber_bias = (double)(float)std::sqrt(16.812);  // const float thHuberNavStateBias  Optimizer.cpp:1439
+        p->huber_mono = (double)(float)std::sqrt(5.99);    // const float thHuber2D            Optimizer.cpp:1541
+    } else {
+        // no kernel on the IMU edges: with an infinite threshold rho' == 1 exactly, and g2o's robust branch
+        // (base_multi_edge.hpp:36-48, base_binary_edge.hpp:61-76) then multiplies by 1.0 -- bit-identical
+        p->huber_pvr = p->huber_bias = INFINITY;
+    }
+}
+
+// Entry 1b: Optimizer::GlobalBundleAdjustmentNavState (Optimizer.cpp:1392-1668), phases "optimize" only
+int vilba_global_ba(vilba_ctx* ctx, const vilba_window* win, int32_t n_iterations, int32_t robust, vilba_result* out,
+                    const volatile uint8_t* stop_flag) {
+    if (!ctx || !out || n_iterations < 0) return VILBA_ERR_ARG;
+    if (ctx->comm) {
+        ctx->err = "vilba_global_ba on a sharded context is not supported";
+        return VILBA_ERR_ARG;
+    }
+    out->n_trace = 0;
+    out->stage2_ran = 0;
+    out->n_outliers_stage1 = 0;
+    out->solve_ms = 0.0;
+    const vilba_params saved = ctx->prm;
+    vilba_global_ba_params(&saved, n_iterations, robust, &ctx->prm);
+    ctx->split = 0;
+    int r = upload_batch(ctx, 1, win);
+    if (r == VILBA_OK) r = solve_batch(ctx, out, stop_flag);
+    if (r == VILBA_OK) r = download_batch(ctx, out);
+    ctx->prm = saved;
     out->status = r;
     return r;
 }

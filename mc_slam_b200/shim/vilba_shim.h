@@ -281,6 +281,8 @@ public:
     void UpdateNormalAndDepth() { ++mnNormalUpdates; }  // geometry bookkeeping is outside the path
     long unsigned int mnId;
     long unsigned int mnBALocalForKF;
+    shim::MatF mPosGBA;  // include/MapPoint.h:127-128
+    long unsigned int mnBAGlobalForKF = 0;
     bool mbBad = false;
     int mnNormalUpdates = 0;
 
@@ -338,9 +340,10 @@ public:
             mIMUPreInt.update(imu._g - bg, imu._a - ba, nextt - imu._t);
         }
     }
-    // KeyFrame::UpdatePoseFromNS (src/KeyFrame.cpp:96-114): camera pose in float32
-    void UpdatePoseFromNS(const shim::MatF& Tbc) {
-        const shim::MatF Rwb = Converter::toCvMat(mNavState.Get_RotMatrix()), Pwb = Converter::toCvMat(mNavState.Get_P());
+    // KeyFrame::UpdatePoseFromNS (src/KeyFrame.cpp:96-114): camera pose in float32.  The global BA's mTcwGBA
+    // (Optimizer.cpp:1646-1652: toCvMatInverse(Twb * Tbc)) is the same float arithmetic on another NavState.
+    static shim::MatF PoseFromNS(const NavState& ns, const shim::MatF& Tbc) {
+        const shim::MatF Rwb = Converter::toCvMat(ns.Get_RotMatrix()), Pwb = Converter::toCvMat(ns.Get_P());
         float Rwc[9], Pwc[3];
         for (int r = 0; r < 3; ++r) {
             for (int c = 0; c < 3; ++c) {
@@ -352,22 +355,28 @@ public:
             for (int k = 0; k < 3; ++k) s += Rwb.at(r, k) * Tbc.at(k, 3);
             Pwc[r] = s + Pwb.at(r);
         }
-        Tcw = shim::MatF(4, 4);
+        shim::MatF T(4, 4);
         for (int r = 0; r < 3; ++r) {
             float s = 0.f;
             for (int c = 0; c < 3; ++c) {
-                Tcw.at(r, c) = Rwc[3 * c + r];  // Rcw = Rwc^T
+                T.at(r, c) = Rwc[3 * c + r];  // Rcw = Rwc^T
                 s += Rwc[3 * c + r] * Pwc[c];
             }
-            Tcw.at(r, 3) = -s;
+            T.at(r, 3) = -s;
         }
-        Tcw.at(3, 3) = 1.f;
+        T.at(3, 3) = 1.f;
+        return T;
     }
+    void UpdatePoseFromNS(const shim::MatF& Tbc) { Tcw = PoseFromNS(mNavState, Tbc); }
     shim::MatF GetPose() const { return Tcw; }
 
     long unsigned int mnId;
     double mTimeStamp;
     long unsigned int mnBALocalForKF, mnBAFixedForKF;
+    // results of a global BA that runs beside the mapping thread (include/KeyFrame.h:263-271)
+    NavState mNavStateGBA;
+    shim::MatF mTcwGBA;
+    long unsigned int mnBAGlobalForKF = 0;
     const float fx, fy, cx, cy;
     std::vector<KeyPoint> mvKeysUn;
     std::vector<float> mvuRight;  // negative => monocular
@@ -386,6 +395,13 @@ inline bool cmpKeyFrameId::operator()(const KeyFrame* a, const KeyFrame* b) cons
 
 struct Map {
     std::mutex mMutexMapUpdate;  // include/Map.h:72
+    // Map::GetAllKeyFrames / GetAllMapPoints (src/Map.cpp:94-105); std::set<T*> order, as in the reference
+    void AddKeyFrame(KeyFrame* pKF) { mspKeyFrames.insert(pKF); }
+    void AddMapPoint(MapPoint* pMP) { mspMapPoints.insert(pMP); }
+    std::vector<KeyFrame*> GetAllKeyFrames() const { return std::vector<KeyFrame*>(mspKeyFrames.begin(), mspKeyFrames.end()); }
+    std::vector<MapPoint*> GetAllMapPoints() const { return std::vector<MapPoint*>(mspMapPoints.begin(), mspMapPoints.end()); }
+    std::set<KeyFrame*> mspKeyFrames;
+    std::set<MapPoint*> mspMapPoints;
 };
 struct LocalMapping {
     void SetMapUpdateFlagInTracking(bool b) { mbMapUpdateFlagForTracking = b; }  // include/LocalMapping.h:52
@@ -423,6 +439,143 @@ class Optimizer {
 public:
     // Same signature and behaviour as the reference (include/Optimizer.h:44-46): phases A/B gather and
     // flatten on the host, C..E run on the GPU behind vilba_local_ba, F writes back.
+    // Optimizer::GlobalBundleAdjustmentNavState (src/Optimizer.cpp:1392-1668): same signature.  The graph build
+    // (:1396-1619) becomes "flatten the whole map into one vilba_window", optimize(nIterations) (:1621-1624) runs
+    // on the GPU through vilba_global_ba, and the write-back (:1626-1667) goes to the live state when nLoopKF == 0
+    // or to the ...GBA members otherwise.
+    static void GlobalBundleAdjustmentNavState(Map* pMap, const shim::MatF& gw, int nIterations, bool* pbStopFlag,
+                                               const unsigned long nLoopKF, const bool bRobust,
+                                               vilba_result* pTrace = NULL) {
+        std::vector<KeyFrame*> vpKFs = pMap->GetAllKeyFrames();
+        const std::vector<MapPoint*> vpMP = pMap->GetAllMapPoints();
+        const double* Tbc = ConfigParam::GetEigTbc();
+        const Vector3d GravityVec = Converter::toVector3d(gw);
+
+        // vertices (:1422-1440): g2o orders the free ones by vertex id = 2 * mnId (+1), i.e. by key-frame id
+        std::vector<KeyFrame*> kfs;
+        for (KeyFrame* pKF : vpKFs)
+            if (!pKF->isBad()) kfs.push_back(pKF);
+        std::sort(kfs.begin(), kfs.end(), cmpKeyFrameId());
+        const int K = (int)kfs.size();
+        if (K == 0) return;
+        std::map<KeyFrame*, int> kfIndex;
+        std::vector<double> kf_state((size_t)VILBA_NS_DOUBLES * K);
+        std::vector<uint8_t> kf_flags(K, VILBA_KF_HAS_BIAS);
+        std::vector<int64_t> kf_id(K);
+        for (int i = 0; i < K; ++i) {
+            kfIndex[kfs[i]] = i;
+            kfs[i]->GetNavState().toFlat(&kf_state[(size_t)VILBA_NS_DOUBLES * i]);
+            kf_id[i] = (int64_t)kfs[i]->mnId;
+            if (kfs[i]->mnId == 0) kf_flags[i] |= VILBA_KF_FIXED;  // vNSPVR / vNSBias ->setFixed(pKF->mnId == 0)
+        }
+        // IMU edges (:1447-1503), in vpKFs order like the reference's loop (the order does not enter the result
+        // beyond floating-point summation order)
+        std::vector<int32_t> imu_i, imu_j;
+        std::vector<double> imu_preint;
+        for (KeyFrame* pKF1 : kfs) {
+            KeyFrame* pKF0 = pKF1->GetPrevKeyFrame();
+            if (!pKF0) {
+                if (pKF1->mnId != 0) std::cerr << "Previous KeyFrame is NULL?" << std::endl;
+                continue;
+            }
+            if (!kfIndex.count(pKF0)) {  // the reference would hand g2o a null vertex here
+                std::cerr << "previous KeyFrame of " << pKF1->mnId << " is bad, global BA skipped" << std::endl;
+                return;
+            }
+            imu_i.push_back(kfIndex.at(pKF0));
+            imu_j.push_back(kfIndex.at(pKF1));
+            const double* raw = pKF1->GetIMUPreInt().raw();
+            imu_preint.insert(imu_preint.end(), raw, raw + VILBA_PREINT_DOUBLES);
+        }
+        // map points and mono edges (:1509-1617); a point without an edge is left out (vbNotIncludedMP)
+        std::vector<MapPoint*> pts;
+        std::vector<double> pt_xyz;
+        std::vector<int32_t> pt_obs_begin(1, 0), obs_kf;
+        std::vector<float> obs_uv, obs_is2;
+        for (MapPoint* pMP : vpMP) {
+            if (pMP->isBad()) continue;
+            const size_t n0 = obs_kf.size();
+            for (auto& ob : pMP->GetObservations()) {
+                KeyFrame* pKF = ob.first;
+                if (pKF->isBad()) continue;
+                if (!(pKF->mvuRight[ob.second] < 0)) {
+                    std::cerr << "Stereo not supported" << std::endl;
+                    continue;
+                }
+                const KeyPoint& kpUn = pKF->mvKeysUn[ob.second];
+                obs_kf.push_back(kfIndex.at(pKF));
+                obs_uv.push_back(kpUn.pt.x), obs_uv.push_back(kpUn.pt.y);
+                obs_is2.push_back(pKF->mvInvLevelSigma2[kpUn.octave]);
+            }
+            if (obs_kf.size() == n0) continue;
+            const Vector3d Pw = Converter::toVector3d(pMP->GetWorldPos());
+            for (int d = 0; d < 3; ++d) pt_xyz.push_back(Pw[d]);
+            pts.push_back(pMP);
+            pt_obs_begin.push_back((int32_t)obs_kf.size());
+        }
+        vilba_window win;
+        std::memset(&win, 0, sizeof(win));
+        win.n_kf = K, win.n_imu = (int32_t)imu_i.size(), win.n_pts = (int32_t)pts.size(), win.n_obs = (int32_t)obs_kf.size();
+        win.kf_state = kf_state.data(), win.kf_flags = kf_flags.data(), win.kf_id = kf_id.data();
+        win.imu_kf_i = imu_i.data(), win.imu_kf_j = imu_j.data(), win.imu_preint = imu_preint.data();
+        win.pt_xyz = pt_xyz.data(), win.pt_obs_begin = pt_obs_begin.data();
+        win.obs_kf = obs_kf.data(), win.obs_uv = obs_uv.data(), win.obs_inv_sigma2 = obs_is2.data();
+        win.fx = kfs.front()->fx, win.fy = kfs.front()->fy, win.cx = kfs.front()->cx, win.cy = kfs.front()->cy;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) win.Rbc[3 * r + c] = Tbc[4 * r + c];
+            win.Pbc[r] = Tbc[4 * r + 3];
+            win.gravity[r] = GravityVec[r];
+        }
+        std::vector<double> out_state(kf_state.size()), out_pts(pt_xyz.size());
+        vilba_result local_res;
+        vilba_result& res = pTrace ? *pTrace : local_res;
+        std::memset(&res, 0, sizeof(res));
+        res.kf_state = out_state.data(), res.pt_xyz = out_pts.data();
+
+        // ---- optimizer.initializeOptimization(); optimizer.optimize(nIterations) on the GPU ----
+        static_assert(sizeof(bool) == 1, "bool* pbStopFlag is polled as a byte");
+        const int st = vilba_global_ba(shim::context(), &win, nIterations, bRobust ? 1 : 0, &res,
+                                       reinterpret_cast<const volatile uint8_t*>(pbStopFlag));
+        if (pTrace) res.kf_state = NULL, res.pt_xyz = NULL;  // scratch does not outlive this call
+        if (st != VILBA_OK) {
+            std::cerr << "vilba_global_ba failed: " << vilba_last_error(shim::context()) << std::endl;
+            return;
+        }
+
+        // ---- recover optimised data (:1626-1667) ----
+        const shim::MatF matTbc = ConfigParam::GetMatTbc();
+        for (int i = 0; i < K; ++i) {
+            KeyFrame* pKF = kfs[i];
+            const double* s = &out_state[(size_t)VILBA_NS_DOUBLES * i];
+            NavState ns_recov = pKF->GetNavState();  // the base biases are not optimised
+            ns_recov.Set_Pos(Vector3d(s[0], s[1], s[2]));
+            ns_recov.Set_Vel(Vector3d(s[3], s[4], s[5]));
+            shim::Quat q;
+            q.w = s[6], q.x = s[7], q.y = s[8], q.z = s[9];
+            ns_recov.Set_Rot(q);
+            ns_recov.Set_DeltaBiasGyr(Vector3d(s[16], s[17], s[18]));
+            ns_recov.Set_DeltaBiasAcc(Vector3d(s[19], s[20], s[21]));
+            if (nLoopKF == 0) {
+                pKF->SetNavState(ns_recov);
+                pKF->UpdatePoseFromNS(matTbc);
+            } else {
+                pKF->mNavStateGBA = ns_recov;
+                pKF->mTcwGBA = KeyFrame::PoseFromNS(ns_recov, matTbc);
+                pKF->mnBAGlobalForKF = nLoopKF;
+            }
+        }
+        for (size_t p = 0; p < pts.size(); ++p) {
+            const Vector3d Pw(out_pts[3 * p], out_pts[3 * p + 1], out_pts[3 * p + 2]);
+            if (nLoopKF == 0) {
+                pts[p]->SetWorldPos(Converter::toCvMat(Pw));
+                pts[p]->UpdateNormalAndDepth();
+            } else {
+                pts[p]->mPosGBA = Converter::toCvMat(Pw);
+                pts[p]->mnBAGlobalForKF = nLoopKF;
+            }
+        }
+    }
+
     static void LocalBundleAdjustmentNavState(KeyFrame* pCurKF, const std::list<KeyFrame*>& lLocalKeyFrames,
                                               bool* pbStopFlag, Map* pMap, shim::MatF& gw, LocalMapping* pLM = NULL,
                                               vilba_result* pTrace = NULL) {

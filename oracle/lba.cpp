@@ -624,16 +624,21 @@ int oracle_local_ba(const vilba_window* win, const vilba_params* params, vilba_r
         prm = *params;
     else
         vilba_default_params_oracle(&prm);
-    if (stop_flag && *stop_flag) {  // Optimizer.cpp:2643-2645: return before optimising, nothing written
+    // GlobalBundleAdjustmentNavState (Optimizer.cpp:1392-1668) is the same graph with one optimize(nIterations):
+    // no early return on the stop flag (g2o then runs zero iterations), no cull, no second stage
+    const bool single_stage = (prm.mode & VILBA_MODE_SINGLE_STAGE) != 0;
+    if (!single_stage && stop_flag && *stop_flag) {  // Optimizer.cpp:2643-2645: return before optimising
         out->status = VILBA_ABORTED;
         return VILBA_ABORTED;
     }
     Problem pb(*win, prm, stop_flag);
+    if (prm.mode & VILBA_MODE_MONO_NOT_ROBUST)  // bRobust == false: no kernel on the mono edges (:1590-1595)
+        std::fill(pb.mono_robust.begin(), pb.mono_robust.end(), 0);
     auto t0 = std::chrono::steady_clock::now();
-    // stage 1: optimizer.initializeOptimization(); optimizer.optimize(5);   (Optimizer.cpp:2647-2648)
+    // stage 1: optimizer.initializeOptimization(); optimizer.optimize(5);   (Optimizer.cpp:2647-2648, :1621-1624)
     int n_active = pb.initialize_optimization();
     pb.optimize(prm.iters_stage1, 1, n_active, out);
-    bool do_more = !(stop_flag && *stop_flag);  // :2650-2654
+    bool do_more = !single_stage && !(stop_flag && *stop_flag);  // :2650-2654
     if (do_more) {
         // :2659-2673  cull + drop the robust kernel of every mono edge
         for (int p_ = 0; p_ < pb.P; ++p_)

@@ -25,7 +25,8 @@ static void wr(FILE* f, const std::vector<T>& v) {
     if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f);
 }
 
-static int run_lba(const char* in, const char* out, bool stop_before) {
+// gba < 0: local BA; otherwise the global BA with nLoopKF = gba
+static int run_lba(const char* in, const char* out, bool stop_before, long gba = -1, bool robust = false) {
     FILE* f = fopen(in, "rb");
     if (!f) return 2;
     auto hdr = rd<int32_t>(f, 4);
@@ -103,7 +104,13 @@ static int run_lba(const char* in, const char* out, bool stop_before) {
     LocalMapping lm;
     bool stop = stop_before;
     vilba_result trace;
-    Optimizer::LocalBundleAdjustmentNavState(local.back(), local, &stop, &map, gw, &lm, &trace);
+    if (gba < 0)
+        Optimizer::LocalBundleAdjustmentNavState(local.back(), local, &stop, &map, gw, &lm, &trace);
+    else {
+        for (auto& k : kfs) map.AddKeyFrame(k.get());
+        for (auto& m : mps) map.AddMapPoint(m.get());
+        Optimizer::GlobalBundleAdjustmentNavState(&map, gw, 10, &stop, (unsigned long)gba, robust, &trace);
+    }
 
     FILE* o = fopen(out, "wb");
     std::vector<double> st((size_t)22 * K);
@@ -117,12 +124,28 @@ static int run_lba(const char* in, const char* out, bool stop_before) {
         for (int d = 0; d < 3; ++d) pw[3 * p + d] = mps[p]->GetWorldPos().at(d);
     std::vector<uint8_t> erased(E);
     for (int e = 0; e < E; ++e) erased[e] = edge_owner[e].second->GetObservations().count(edge_owner[e].first) ? 0 : 1;
-    std::vector<int32_t> meta = {lm.mbMapUpdateFlagForTracking ? 1 : 0, stop_before ? 0 : trace.n_trace,
-                                 stop_before ? 0 : trace.stage2_ran, P ? mps[0]->mnNormalUpdates : 0};
+    const bool have_trace = !stop_before || gba >= 0;  // the local BA returns before touching *pTrace
+    std::vector<int32_t> meta = {lm.mbMapUpdateFlagForTracking ? 1 : 0, have_trace ? trace.n_trace : 0,
+                                 have_trace ? trace.stage2_ran : 0, P ? mps[0]->mnNormalUpdates : 0};
     std::vector<double> chi(64, 0.0);
-    if (!stop_before)
+    if (have_trace)
         for (int i = 0; i < trace.n_trace && i < 64; ++i) chi[i] = trace.trace[i].chi2_final;
     wr(o, meta), wr(o, st), wr(o, tcw), wr(o, pw), wr(o, erased), wr(o, chi);
+    if (gba >= 0) {  // the ...GBA members (Optimizer.cpp:1643-1665)
+        std::vector<double> stg((size_t)22 * K, 0.0);
+        std::vector<float> tcwg((size_t)16 * K, 0.f), pg((size_t)3 * P, 0.f);
+        std::vector<int64_t> tag(K + P);
+        for (int k = 0; k < K; ++k) {
+            kfs[k]->mNavStateGBA.toFlat(&stg[(size_t)22 * k]);
+            for (int i = 0; i < 16 && !kfs[k]->mTcwGBA.empty(); ++i) tcwg[(size_t)16 * k + i] = kfs[k]->mTcwGBA.d[i];
+            tag[k] = (int64_t)kfs[k]->mnBAGlobalForKF;
+        }
+        for (int p = 0; p < P; ++p) {
+            for (int d = 0; d < 3 && !mps[p]->mPosGBA.empty(); ++d) pg[3 * p + d] = mps[p]->mPosGBA.at(d);
+            tag[K + p] = (int64_t)mps[p]->mnBAGlobalForKF;
+        }
+        wr(o, stg), wr(o, tcwg), wr(o, pg), wr(o, tag);
+    }
     fclose(o);
     return 0;
 }
@@ -174,6 +197,8 @@ int main(int argc, char** argv) {
     if (argc < 4) return 1;
     try {
         if (std::string(argv[1]) == "lba") return run_lba(argv[2], argv[3], argc > 4);
+        if (std::string(argv[1]) == "gba")  // gba in out nLoopKF robust [stop]
+            return run_lba(argv[2], argv[3], argc > 6, std::atol(argv[4]), std::atoi(argv[5]) != 0);
         if (std::string(argv[1]) == "preint") return run_preint(argv[2], argv[3]);
     } catch (const std::exception& e) {
         fprintf(stderr, "error: %s\n", e.what());

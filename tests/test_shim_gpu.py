@@ -134,3 +134,77 @@ def test_keyframe_compute_preint(driver, vilba, oracle, tmp_path):
         scale = np.abs(ref[:, 60:141]).max(axis=1, keepdims=True)
         assert np.all(np.abs(got[:, 60:141] - ref[:, 60:141]) <= 1e-9 * scale)
         assert np.allclose(got[:, 141], ref[:, 141], rtol=1e-12)
+
+
+def _read_gba(path, w):
+    K, P, E = w.n_kf, w.n_pts, w.n_obs
+    with open(path, "rb") as f:
+        f.seek(4 * 4 + 8 * 22 * K + 4 * 16 * K + 4 * 3 * P + E + 8 * 64)
+        stg = np.fromfile(f, np.float64, 22 * K).reshape(K, 22)
+        tcwg = np.fromfile(f, np.float32, 16 * K).reshape(K, 4, 4)
+        pg = np.fromfile(f, np.float32, 3 * P).reshape(P, 3)
+        tag = np.fromfile(f, np.int64, K + P)
+    return stg, tcwg, pg, tag
+
+
+def _global_map():
+    w = synth.make_window(n_kf=8, n_pts=400, mean_run=5.0, seed=synth.SEED_BASE + 41)
+    w.kf_id = np.arange(w.n_kf, dtype=np.int64)  # the first key-frame of the map has mnId 0 and is the fixed one
+    return w
+
+
+@pytest.mark.parametrize("robust", [0, 1])
+def test_global_ba_entry_point_writes_the_live_state(driver, vilba, tmp_path, robust):
+    """Optimizer::GlobalBundleAdjustmentNavState with nLoopKF == 0 (src/Optimizer.cpp:1637-1641,1657-1660)."""
+    w = _global_map()
+    _write_window(tmp_path / "in.bin", w)
+    subprocess.check_call([driver, "gba", str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), "0", str(robust)])
+    meta, st, tcw, pw, erased, chi = _read_result(tmp_path / "out.bin", w)
+    stg, tcwg, pg, tag = _read_gba(tmp_path / "out.bin", w)
+    with vilba.Context(0) as ctx:
+        r = ctx.global_ba(w, n_iterations=10, robust=bool(robust))
+    assert meta[1] == len(r.trace) and meta[2] == 0 and meta[3] == 1
+    for i, t in enumerate(r.trace):
+        assert abs(chi[i] - t["chi2_final"]) <= 1e-9 * abs(t["chi2_final"])
+    assert np.abs(st[:, :10] - r.kf_state[:, :10]).max() < 1e-9 and np.abs(st[:, 16:] - r.kf_state[:, 16:]).max() < 1e-9
+    assert np.array_equal(st[0], w.kf_state[0])  # mnId 0 is fixed
+    assert np.array_equal(st[:, 10:16], w.kf_state[:, 10:16])
+    assert np.abs(pw - r.pt_xyz.astype(np.float32)).max() <= 2e-6
+    assert not erased.any()  # the global BA erases nothing
+    assert tcw[:, 3, 3].tolist() == [1.0] * w.n_kf  # UpdatePoseFromNS on every key-frame
+    assert not tag.any() and not tcwg.any() and not pg.any()
+
+
+def test_global_ba_entry_point_beside_the_mapping_thread(driver, vilba, tmp_path):
+    """nLoopKF != 0: results go to mNavStateGBA / mTcwGBA / mPosGBA, the live map is untouched (:1643-1665)."""
+    w = _global_map()
+    _write_window(tmp_path / "in.bin", w)
+    subprocess.check_call([driver, "gba", str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), "7", "0"])
+    meta, st, tcw, pw, erased, chi = _read_result(tmp_path / "out.bin", w)
+    stg, tcwg, pg, tag = _read_gba(tmp_path / "out.bin", w)
+    with vilba.Context(0) as ctx:
+        r = ctx.global_ba(w, n_iterations=10, robust=False)
+    assert np.array_equal(st, w.kf_state) and np.array_equal(pw, w.pt_xyz.astype(np.float32)) and not tcw.any()
+    assert meta[3] == 0  # no UpdateNormalAndDepth
+    assert (tag == 7).all()
+    assert np.abs(stg[:, :10] - r.kf_state[:, :10]).max() < 1e-9 and np.abs(stg[:, 16:] - r.kf_state[:, 16:]).max() < 1e-9
+    assert np.array_equal(stg[:, 10:16], w.kf_state[:, 10:16])
+    assert np.abs(pg - r.pt_xyz.astype(np.float32)).max() <= 2e-6
+    from scipy.spatial.transform import Rotation
+    for k in range(w.n_kf):
+        q = r.kf_state[k, 6:10]
+        Rwc = Rotation.from_quat([q[1], q[2], q[3], q[0]]).as_matrix() @ w.Rbc
+        Pwc = Rotation.from_quat([q[1], q[2], q[3], q[0]]).as_matrix() @ w.Pbc + r.kf_state[k, 0:3]
+        assert np.abs(tcwg[k][:3, :3] - Rwc.T).max() < 1e-5 and np.abs(tcwg[k][:3, 3] + Rwc.T @ Pwc).max() < 1e-4
+
+
+def test_global_ba_entry_point_with_the_stop_flag_up(driver, tmp_path):
+    """g2o runs zero iterations and the function still writes the (unchanged) estimates back."""
+    w = _global_map()
+    _write_window(tmp_path / "in.bin", w)
+    subprocess.check_call([driver, "gba", str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), "0", "0", "stop"])
+    meta, st, tcw, pw, erased, chi = _read_result(tmp_path / "out.bin", w)
+    assert meta[1] == 0 and meta[3] == 1
+    assert np.abs(st - w.kf_state).max() < 1e-15  # quaternion -> matrix -> quaternion of Set_Rot
+    assert np.array_equal(pw, w.pt_xyz.astype(np.float32))
+    assert tcw[:, 3, 3].tolist() == [1.0] * w.n_kf

@@ -188,7 +188,84 @@ __global__ void k_dfma_tput(double* out, long long* cyc, double a, double b) {
     out[threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[0] = (t1 - t0);
 }
+// FP64 tensor path: mma.sync m8n8k4 (DMMA), 8 independent accumulator fragments per warp
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void k_dmma_tput(double* out, long long* cyc, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = out[threadIdx.x] + i, c[i][1] = 0.5 * i;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 128; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[0] = (t1 - t0);
+}
+__global__ void k_dmma_lat(double* out, long long* cyc, double a, double b) {
+    double c0 = out[threadIdx.x], c1 = 1.0;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) { dmma884(c0, c1, a, b); dmma884(c0, c1, a, b); dmma884(c0, c1, a, b); dmma884(c0, c1, a, b); }
+    long long t1 = clock64();
+    out[threadIdx.x] = c0 + c1;
+    if (threadIdx.x == 0) cyc[0] = (t1 - t0);
+}
+// shared memory -> register bandwidth: every lane loads the SAME address (broadcast) or its own
+template <int WIDTH, bool BCAST>
+__global__ void k_lds_bw(double* out, long long* cyc) {
+    __shared__ __align__(16) double s[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s[i] = i;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int base = ((it + 4 * k) & 31) * 64 + (BCAST ? 0 : lane * (WIDTH / 8));
+            if (WIDTH == 16) { const double2 v = *reinterpret_cast<const double2*>(s + base); acc += v.x + v.y; }
+            else acc += s[base];
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    out[threadIdx.x] = acc;
+    if (threadIdx.x == 0) cyc[0] = (t1 - t0);
+}
 int main() {
+    {
+        double* o; long long* cy; cudaMalloc(&o, 1024 * 8); cudaMemset(o, 0, 8192); cudaMallocManaged(&cy, 64);
+        for (int nt : {32, 128, 256, 512, 1024}) {
+            k_dmma_tput<<<1, nt>>>(o, cy, 1.0000001, 1e-9); cudaDeviceSynchronize();
+            double mmas = (double)(nt / 32) * 128 * 32;  // warp-level m8n8k4 (256 FMAs each)
+            printf("DMMA m8n8k4 throughput, %4d threads/SM: %.2f cycles per mma per SM, %.1f FMA/clk/SM\n", nt, (double)cy[0] / mmas, mmas * 256 / (double)cy[0]);
+        }
+        k_dmma_lat<<<1, 32>>>(o, cy, 1.0000001, 1e-9); cudaDeviceSynchronize();
+        printf("dependent DMMA m8n8k4: %.1f cycles\n", (double)cy[0] / 1024);
+        for (int nt : {32, 256, 1024}) {
+            k_lds_bw<8, true><<<1, nt>>>(o, cy); cudaDeviceSynchronize();
+            printf("LDS.64 broadcast,  %4d threads: %.2f cycles per warp-load per SM\n", nt, (double)cy[0] / ((nt / 32) * 1024.0));
+            k_lds_bw<16, true><<<1, nt>>>(o, cy); cudaDeviceSynchronize();
+            printf("LDS.128 broadcast, %4d threads: %.2f cycles per warp-load per SM\n", nt, (double)cy[0] / ((nt / 32) * 1024.0));
+            k_lds_bw<8, false><<<1, nt>>>(o, cy); cudaDeviceSynchronize();
+            printf("LDS.64 per lane,   %4d threads: %.2f cycles per warp-load per SM\n", nt, (double)cy[0] / ((nt / 32) * 1024.0));
+            k_lds_bw<16, false><<<1, nt>>>(o, cy); cudaDeviceSynchronize();
+            printf("LDS.128 per lane,  %4d threads: %.2f cycles per warp-load per SM\n", nt, (double)cy[0] / ((nt / 32) * 1024.0));
+        }
+    }
     {
         double* o; long long* cy; cudaMalloc(&o, 1024 * 8); cudaMemset(o, 0, 8192); cudaMallocManaged(&cy, 64);
         for (int nt : {32, 128, 256, 512, 1024}) {
