@@ -194,6 +194,8 @@ struct LaunchDims {
     int sp_grid;          // ... and the points into this many subsets (= partial sums per window)
     int sp_tile_pts;      // map points per shared-memory tile
     int sp_pair_lanes;    // 1: one lane per block pair (36 accumulators), one CTA covers all pairs of the window
+    int sp_mma;           // 1: tile kernel with one warp per hit on the FP64 MMA (operands Z = W G, D^-1 = G G^T); an option, not the default
+    int sp_tile_edges;    // ... its shared-memory tile holds this many edges (the largest tile of the batch)
     int chol_cluster;     // CTAs of the Cholesky cluster
     int chol_la;          // 1: look-ahead cluster kernel with the trailing matrix in shared memory (chol_la.cu)
     int chol_n;           // largest reduced system of the batch (sizes the shared memory of chol_la)
@@ -211,6 +213,8 @@ size_t chol_smem_bytes(int n);
 bool schur_tile_fits(int K, int n_free);   // the tile-scan Schur kernel handles windows of <= 32 key-frames
 size_t schur_tile_smem_bytes(int max_K, int tile_pts);
 size_t schur_tile_rec_doubles(int P);
+int schur_mma_units(int n_free);                  // warps of the tensor-pipe kernel that cover all block pairs
+size_t schur_mma_smem_bytes(int tile_edges, int tile_pts);
 int schur_pair_lanes(int n_free);                 // lanes (= threads) of the lane-per-pair tile kernel
 size_t schur_pair_partial_doubles(int n_free);    // size of one of its partial sums
 size_t schur_tile_hdr_words(int P, int tile_pts);

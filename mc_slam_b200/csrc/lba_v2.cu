@@ -598,7 +598,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 // one warp per tile, one lane per map point
-__global__ void __launch_bounds__(256) schur_rec_kernel(const DevWindow* __restrict__ wp, int tile_pts) {
+__global__ void __launch_bounds__(256) schur_rec_kernel(const DevWindow* __restrict__ wp, int tile_pts, int factor_form) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_TRIAL) return;
     const int lane = threadIdx.x & 31;
@@ -618,14 +618,39 @@ __global__ void __launch_bounds__(256) schur_rec_kernel(const DevWindow* __restr
                 if (!(rw & OBS_CULLED) && w.kf_block[kf] >= 0) fm |= 1u << kf;
             }
             const double* H = w.Hll + 6 * (size_t)p;
-            bool ok;
-            const S3 Dinv = s3_inverse(S3{H[0] + lambda, H[1], H[2], H[3] + lambda, H[4], H[5] + lambda}, ok);
-            const V3 db = s3_mul(Dinv, ld3(w.bl + 3 * (size_t)p));
             double* d = w.ts_rec + (size_t)kTsRecDoubles * p;
-            d[0] = Dinv.xx, d[1] = Dinv.xy, d[2] = Dinv.xz, d[3] = Dinv.yy, d[4] = Dinv.yz, d[5] = Dinv.zz;
-            d[6] = db.x, d[7] = db.y, d[8] = db.z;
-            unsigned* u = reinterpret_cast<unsigned*>(d + 9);
-            u[0] = am, u[1] = fm, u[2] = (unsigned)(e0 - w.pt_obs_begin[g * tile_pts]), u[3] = 0u;
+            const unsigned eb = (unsigned)(e0 - w.pt_obs_begin[g * tile_pts]);
+            if (factor_form) {
+                // D = H_ll + lambda I = L L^T (positive definite: H_ll is a sum of J^T w J with w >= 0, lambda > 0), so
+                // D^-1 = G G^T with G = L^-T upper triangular.  With Z = W G the landmark term of the reduced system is
+                // W_a D^-1 W_b^T = Z_a Z_b^T and W_a D^-1 b_l = Z_a (G^T b_l): one operand array instead of W and W D^-1.
+                const double xx = H[0] + lambda, xy = H[1], xz = H[2], yy = H[3] + lambda, yz = H[4], zz = H[5] + lambda;
+                const double m00 = rsqrt(xx);
+                const double l10 = xy * m00, l20 = xz * m00;
+                const double m11 = rsqrt(yy - l10 * l10);
+                const double l21 = (yz - l20 * l10) * m11;
+                const double m22 = rsqrt(zz - l20 * l20 - l21 * l21);
+                double g00 = m00, g11 = m11, g22 = m22;
+                double g01 = -l10 * m00 * m11;            // (L^-1)(1,0)
+                double g12 = -l21 * m11 * m22;            // (L^-1)(2,1)
+                double g02 = -(l20 * m00 + l21 * g01) * m22;  // (L^-1)(2,0)
+                if (!(isfinite(g00) && isfinite(g11) && isfinite(g22)))  // not positive definite: the point drops out
+                    g00 = g01 = g02 = g11 = g12 = g22 = 0.0;
+                const V3 b = ld3(w.bl + 3 * (size_t)p);
+                unsigned* u = reinterpret_cast<unsigned*>(d);
+                u[0] = am, u[1] = fm, u[2] = eb, u[3] = (unsigned)(e1 - e0);
+                d[2] = g00, d[3] = g01, d[4] = g02, d[5] = g11, d[6] = g12, d[7] = g22;
+                d[8] = g00 * b.x, d[9] = fma(g11, b.y, g01 * b.x), d[10] = fma(g22, b.z, fma(g12, b.y, g02 * b.x));  // G^T b_l
+                d[11] = 0.0;
+            } else {
+                bool ok;
+                const S3 Dinv = s3_inverse(S3{H[0] + lambda, H[1], H[2], H[3] + lambda, H[4], H[5] + lambda}, ok);
+                const V3 db = s3_mul(Dinv, ld3(w.bl + 3 * (size_t)p));
+                d[0] = Dinv.xx, d[1] = Dinv.xy, d[2] = Dinv.xz, d[3] = Dinv.yy, d[4] = Dinv.yz, d[5] = Dinv.zz;
+                d[6] = db.x, d[7] = db.y, d[8] = db.z;
+                unsigned* u = reinterpret_cast<unsigned*>(d + 9);
+                u[0] = am, u[1] = fm, u[2] = eb, u[3] = 0u;
+            }
         }
         unsigned mine = 0;
 #pragma unroll 4
@@ -763,6 +788,201 @@ __global__ void __launch_bounds__(512) schur_tile_kernel(const DevWindow* __rest
 #pragma unroll
         for (int c = 0; c < 6; ++c) d[c] = acc[s2][c];
         if (a == b) part[(size_t)w.n_pairs * 36 + 6 * a + r] = rb[s2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-pipe variant: ONE WARP PER HIT.  A block pair's contribution of one point is the 6x6x3 product
+// Z_a Z_b^T, which is one m8n8k4 FP64 MMA with the operands padded by zeros: every lane loads ONE double of Z_a
+// and ONE of Z_b (18 distinct words of a 144-byte block, no replication across lanes) where the row-per-lane
+// kernels load 21 and issue 21 DFMA per lane.  The FP64 pipe does the same number of multiply-adds per clock
+// either way (tools/ubench_fp64.cu); what the MMA buys is 14 instead of 66 issue slots per warp-level hit, half
+// the shared-memory wavefronts, and no idle lane groups.  Column 6 of the B operand carries G^T b_l, so that the
+// diagonal pairs produce the right-hand side Z_a (G^T b_l) in column 6 of their accumulator for free.
+// Measured (profiles/r2_schur_variants.md): parity-identical, 1.04 ms per 64-window launch against 0.96 ms for the
+// row-per-lane-group kernel -- the per-(pair, tile) set-up and the list round trip cost what the MMA saves, so it is
+// an option (env VILBA_SP_MMA=1), not the default.
+// A warp owns up to kMmaPairs block pairs (two accumulator registers per lane and pair), interleaved by distance
+// so that close (many hits) and distant pairs mix.  Per tile the lanes first compute, each for one map point, the
+// packed edge indices of (a, b) -- the bookkeeping of ALL hits of the pair in the tile in one go -- and the hit loop
+// takes them with a shuffle.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMmaPairs = 6;
+struct TmLayout {
+    size_t rec, hdr, buf_bytes, cpad, zero, ents, total;
+};
+__host__ __device__ static inline TmLayout tm_layout(int tile_edges, int tile_pts) {
+    TmLayout L;
+    L.rec = (size_t)tile_edges * 144;
+    L.hdr = L.rec + (size_t)tile_pts * 8 * kTsRecDoubles;
+    L.buf_bytes = (L.hdr + 4 * kTsHdrWords + 127) / 128 * 128;
+    L.cpad = 2 * L.buf_bytes;                         // G^T b_l per edge (24 bytes), current tile only
+    L.zero = L.cpad + ((size_t)tile_edges * 24 + 15) / 16 * 16;
+    L.ents = L.zero + 16;                             // per warp: the packed hit list of the pair at hand (32 words)
+    L.total = L.ents + 16 * 128 + 64;
+    return L;
+}
+size_t schur_mma_smem_bytes(int tile_edges, int tile_pts) { return tm_layout(tile_edges, tile_pts).total; }
+int schur_mma_units(int n_free) { return (n_free * (n_free + 1) / 2 + kMmaPairs - 1) / kMmaPairs; }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(512, 2) schur_mma_kernel(const DevWindow* __restrict__ wp, int sets, int tile_pts, int tile_edges) {
+    const DevWindow w = wp[blockIdx.y];  // one window per grid row
+    if (w.lm->phase != PH_TRIAL) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar[2];
+    const TmLayout L = tm_layout(tile_edges, tile_pts);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int set = blockIdx.x % sets, psub = blockIdx.x / sets, npsub = gridDim.x / sets;
+    const int nf = w.n_free;
+    const int units = sets * warps, unit = set * warps + warp;
+    // the block pairs of this warp: q = i * units + unit in the order of increasing distance b - a
+    unsigned pk[kMmaPairs];  // key-frame index of a | key-frame index of b << 8
+    int my_pairs = 0;
+#pragma unroll
+    for (int i = 0; i < kMmaPairs; ++i) {
+        pk[i] = 0;
+        const int q = i * units + unit;
+        if (q < w.n_pairs) {
+            int a, b;
+            ts_pair_by_distance(q, nf, a, b);
+            pk[i] = (unsigned)w.blk_kf[a] | ((unsigned)w.blk_kf[b] << 8);
+            my_pairs = i + 1;
+        }
+    }
+    double acc[kMmaPairs][2];
+#pragma unroll
+    for (int i = 0; i < kMmaPairs; ++i) acc[i][0] = acc[i][1] = 0.0;
+    // operand fragments of mma.m8n8k4: A(row = lane / 4, k = lane % 4), B(k = lane % 4, col = lane / 4)
+    const int frow = lane >> 2, fk = lane & 3;
+    const bool zlane = frow < 6 && fk < 3;       // an entry of the 6x3 block
+    const bool clane = frow == 6 && fk < 3;      // B only: G^T b_l in column 6
+    const unsigned zoff = (unsigned)(3 * frow + fk) * 8u;
+    const unsigned strideA = zlane ? 144u : 0u, strideB = zlane ? 144u : (clane ? 24u : 0u);
+    const unsigned smem0 = smem_u32(smem_raw);
+    const unsigned zero_addr = smem0 + (unsigned)L.zero;
+    if (threadIdx.x < 2) reinterpret_cast<double*>(smem_raw + L.zero)[threadIdx.x] = 0.0;
+    unsigned* ents = reinterpret_cast<unsigned*>(smem_raw + L.ents) + 32 * warp;
+    if (lane < 32) ents[lane] = 0u;
+
+    const int ntile = (w.P + tile_pts - 1) / tile_pts;
+    const int g_begin = (int)((long long)ntile * psub / npsub), g_end = (int)((long long)ntile * (psub + 1) / npsub);
+    const int nt = g_end - g_begin;
+    const bool leader = threadIdx.x == 0;
+    if (leader) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int g, int b2, int e_lo, int e_hi) {
+        unsigned char* buf = smem_raw + (size_t)b2 * L.buf_bytes;
+        const int p0 = g * tile_pts, np = min(tile_pts, w.P - p0);
+        const unsigned wbytes = 144u * (unsigned)(e_hi - e_lo), rbytes = 8u * kTsRecDoubles * (unsigned)np, hbytes = 4u * kTsHdrWords;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic-proxy accesses of the buffer
+        mbar_expect_tx(&bar[b2], wbytes + rbytes + hbytes);
+        if (wbytes) tma_load_1d(buf, w.W + 18 * (size_t)e_lo, wbytes, &bar[b2]);
+        tma_load_1d(buf + L.rec, w.ts_rec + (size_t)kTsRecDoubles * p0, rbytes, &bar[b2]);
+        tma_load_1d(buf + L.hdr, w.ts_hdr + (size_t)kTsHdrWords * g, hbytes, &bar[b2]);
+    };
+    auto tile_edges_of = [&](int t, int& e_lo, int& e_hi) {
+        e_lo = e_hi = 0;
+        if (leader && t < nt) {
+            const int p0 = (g_begin + t) * tile_pts;
+            e_lo = w.pt_obs_begin[p0];
+            e_hi = w.pt_obs_begin[min(p0 + tile_pts, w.P)];
+        }
+    };
+    int e_lo_n, e_hi_n, e_lo_nn, e_hi_nn;
+    tile_edges_of(0, e_lo_n, e_hi_n);
+    if (leader && nt > 0) issue(g_begin, 0, e_lo_n, e_hi_n);
+    tile_edges_of(1, e_lo_n, e_hi_n);
+
+    for (int t = 0; t < nt; ++t) {
+        if (leader && t + 1 < nt) issue(g_begin + t + 1, (t + 1) & 1, e_lo_n, e_hi_n);
+        tile_edges_of(t + 2, e_lo_nn, e_hi_nn);
+        unsigned char* buf = smem_raw + (size_t)(t & 1) * L.buf_bytes;
+        double* bZ = reinterpret_cast<double*>(buf);
+        const double* bRec = reinterpret_cast<const double*>(buf + L.rec);
+        const unsigned* colmask = reinterpret_cast<const unsigned*>(buf + L.hdr);
+        double* cpad = reinterpret_cast<double*>(smem_raw + L.cpad);
+        const int np = min(tile_pts, w.P - (g_begin + t) * tile_pts);
+        mbar_wait(&bar[t & 1], (unsigned)((t >> 1) & 1));
+        // ---- W -> Z = W G in place, G^T b_l beside every edge: task = (point, row of the 6x3 blocks, one edge in four) ----
+        for (int q = threadIdx.x; q < np * 24; q += blockDim.x) {
+            const int l = q / 24, rem = q - 24 * l, j = rem >> 2, sl = rem & 3;
+            const double* d = bRec + kTsRecDoubles * l;
+            const uint4 hd = *reinterpret_cast<const uint4*>(d);
+            const double2 ga = *reinterpret_cast<const double2*>(d + 2), gb = *reinterpret_cast<const double2*>(d + 4),
+                          gc = *reinterpret_cast<const double2*>(d + 6);
+            const double c0 = d[8], c1 = d[9], c2 = d[10];
+            for (unsigned e = sl; e < hd.w; e += 4) {
+                double* z = bZ + 18 * (hd.z + e) + 3 * j;
+                const double w0 = z[0], w1 = z[1], w2 = z[2];
+                z[0] = w0 * ga.x;
+                z[1] = fma(w1, gb.y, w0 * ga.y);
+                z[2] = fma(w2, gc.y, fma(w1, gc.x, w0 * gb.x));
+                if (j == 0) {
+                    double* c = cpad + 3 * (hd.z + e);
+                    c[0] = c0, c[1] = c1, c[2] = c2;
+                }
+            }
+        }
+        __syncthreads();
+        // this lane's map point: observers and first edge
+        unsigned am_l = 0, eb_l = 0;
+        if (lane < np) {
+            const uint4 hd = *reinterpret_cast<const uint4*>(bRec + kTsRecDoubles * lane);
+            am_l = hd.x, eb_l = hd.z;
+        }
+        const unsigned bufaddr = smem0 + (unsigned)((size_t)(t & 1) * L.buf_bytes);
+        const unsigned baseA = zlane ? bufaddr + zoff : zero_addr;
+        const unsigned baseB = zlane ? bufaddr + zoff : (clane ? smem0 + (unsigned)L.cpad + 8u * fk : zero_addr);
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int i = 0; i < kMmaPairs; ++i) {
+            if (i >= my_pairs) break;  // warp-uniform
+            const unsigned ka = pk[i] & 255u, kb = pk[i] >> 8;
+            const unsigned hits = colmask[ka] & colmask[kb];
+            if (!hits) continue;
+            // edge of a | edge of b << 16 for the point of this lane; the hits are packed to the front of the warp's list
+            const unsigned ent = (eb_l + __popc(am_l & ((1u << ka) - 1u))) | ((eb_l + __popc(am_l & ((1u << kb) - 1u))) << 16);
+            __syncwarp();  // the list of the previous pair has been read
+            if ((hits >> lane) & 1u) ents[__popc(hits & lt)] = ent;
+            __syncwarp();
+            const int n = __popc(hits);
+            double c0 = acc[i][0], c1 = acc[i][1];
+            for (int j = 0; j < n; j += 2) {  // two hits per round: four independent loads in flight
+                const uint2 e2 = *reinterpret_cast<const uint2*>(ents + j);
+                double a0, b0, a1, b1;
+                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(a0) : "r"(baseA + (e2.x & 0xffffu) * strideA));
+                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(b0) : "r"(baseB + (e2.x >> 16) * strideB));
+                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(a1) : "r"(baseA + (e2.y & 0xffffu) * strideA));
+                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(b1) : "r"(baseB + (e2.y >> 16) * strideB));
+                dmma884(c0, c1, a0, b0);
+                if (j + 1 < n) dmma884(c0, c1, a1, b1);  // (the entry beyond the list is stale but a valid edge of the tile)
+            }
+            acc[i][0] = c0, acc[i][1] = c1;
+        }
+        e_lo_n = e_lo_nn, e_hi_n = e_hi_nn;
+        __syncthreads();  // tile t consumed: its buffer may be refilled
+    }
+    // accumulator fragment: C(row = lane / 4, col = 2 (lane % 4) + {0, 1}); column 6 of a diagonal pair is the rhs
+    double* part = w.schur_partial + (size_t)psub * sp_acc_doubles(nf);
+#pragma unroll
+    for (int i = 0; i < kMmaPairs; ++i) {
+        const int q = i * units + unit;
+        if (i >= my_pairs || q >= w.n_pairs) break;
+        int a, b;
+        ts_pair_by_distance(q, nf, a, b);
+        if (frow < 6) {
+            double* d = part + (size_t)(a * nf - a * (a - 1) / 2 + (b - a)) * 36 + 6 * frow;
+            if (fk < 3) d[2 * fk] = acc[i][0], d[2 * fk + 1] = acc[i][1];
+            else if (a == b) part[(size_t)w.n_pairs * 36 + 6 * a + frow] = acc[i][0];
+        }
     }
 }
 
@@ -1010,6 +1230,8 @@ cudaError_t configure_kernels(const LaunchDims& d) {
     if (e != cudaSuccess) return e;
     e = opt_in_max_smem(schur_tile_kernel);
     if (e != cudaSuccess) return e;
+    e = opt_in_max_smem(schur_mma_kernel);
+    if (e != cudaSuccess) return e;
     e = opt_in_max_smem(schur_tile_pair_kernel);
     if (e != cudaSuccess) return e;
     e = configure_point_kernels(d);
@@ -1042,8 +1264,11 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     // ---- one LM trial (skipped unless phase == TRIAL) ----
     if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
     if (d.sp_warps > 0) {
-        schur_rec_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_tile_pts);
-        if (d.sp_pair_lanes)
+        schur_rec_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_tile_pts, d.sp_mma);
+        if (d.sp_mma)
+            schur_mma_kernel<<<dim3(d.sp_grid * d.sp_sets, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_sets, d.sp_tile_pts,
+                                                                                                      d.sp_tile_edges);
+        else if (d.sp_pair_lanes)
             schur_tile_pair_kernel<<<dim3(d.sp_grid, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_tile_pts);
         else
             schur_tile_kernel<<<dim3(d.sp_grid * d.sp_sets, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_sets, d.sp_tile_pts);

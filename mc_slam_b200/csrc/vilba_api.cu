@@ -86,6 +86,7 @@ struct Layout {
 struct WinMeta {
     int K = 0, NI = 0, P = 0, E = 0, n_free = 0, n = 0, n_pairs = 0;
     size_t n_triples = 0;
+    int tile_edges[3] = {0, 0, 0};  // most edges in a tile of 32 / 16 / 8 map points
     Layout L;
     size_t in_base = 0, out_base = 0, wk_base = 0;
 };
@@ -200,6 +201,8 @@ struct vilba_ctx {
     int sp_grid_cap = 74;            // env VILBA_SP_GRID: point subsets per window of the tile-scan Schur kernel
     int sp_pair_lanes = 0;           // env VILBA_SP_PAIR=1: lane-per-pair variant of the tile-scan Schur kernel
     int sp_sets = 0;                 // env VILBA_SP_SETS: block-pair subsets (0 = automatic)
+    int sp_mma = 0;                  // env VILBA_SP_MMA=1: tile kernel with one warp per hit on the FP64 MMA (lba_v2.cu)
+    int tile_edges[3] = {0, 0, 0};   // most edges in a tile of 32 / 16 / 8 map points over the current batch
     int cap_K = 0, cap_nf = 0, cap_n = 0;  // capacities the shared-memory sizes were configured for
     std::vector<GraphEntry> graphs;        // one captured LM slot per launch geometry
     bool use_graph = true;                 // env VILBA_GRAPH=0 launches the slot kernels one by one
@@ -368,6 +371,28 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
         if (const char* e = std::getenv("VILBA_SP_PSUB")) d.sp_grid = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("VILBA_SP_TILE")) d.sp_tile_pts = std::max(2, std::min(d.sp_tile_pts, std::atoi(e)));
         d.smem_sp = schur_tile_smem_bytes(max_K, d.sp_tile_pts);
+        d.sp_mma = 0, d.sp_tile_edges = 0;
+        if (ctx->sp_mma && !d.sp_pair_lanes && ctx->tile_edges[0] > 0) {
+            // tensor-pipe kernel: the largest tile (32, 16 or 8 map points) whose buffers leave room for two CTAs per SM;
+            // the warps that cover all block pairs are cut into `sets` CTAs of at most 16
+            const int tp[3] = {32, 16, 8};
+            int pick = 0;
+            while (pick < 2 && schur_mma_smem_bytes(ctx->tile_edges[pick], tp[pick]) > 110 * 1024) ++pick;
+            if (const char* e = std::getenv("VILBA_SP_TILE")) pick = std::atoi(e) >= 32 ? 0 : (std::atoi(e) >= 16 ? 1 : 2);
+            if (schur_mma_smem_bytes(ctx->tile_edges[pick], tp[pick]) <= 227 * 1024) {
+                const int warps_all = schur_mma_units(max_nf);
+                int sets = ctx->sp_sets > 0 ? ctx->sp_sets : std::max(1, (warps_all + 15) / 16);
+                sets = std::max(sets, (warps_all + 15) / 16);
+                d.sp_mma = 1;
+                d.sp_sets = sets;
+                d.sp_warps = (warps_all + sets - 1) / sets;
+                d.sp_tile_pts = tp[pick];
+                d.sp_tile_edges = ctx->tile_edges[pick];
+                d.sp_grid = std::max(1, std::min(ctx->sp_grid_cap, 2 * sm / (d.sp_sets * n_win)));
+                if (const char* e = std::getenv("VILBA_SP_PSUB")) d.sp_grid = std::max(1, std::atoi(e));
+                d.smem_sp = schur_mma_smem_bytes(d.sp_tile_edges, d.sp_tile_pts);
+            }
+        }
     }
     // Cholesky.  Large reduced systems: blocked factorisation over the whole GPU (chol_big.cu); small ones: one cluster
     // per window, as many CTAs as the machine has to spare (one 8-CTA cluster for a single window, smaller clusters when
@@ -658,6 +683,13 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
             const size_t mm = (size_t)(w->pt_obs_begin[p + 1] - w->pt_obs_begin[p]);
             m.n_triples += mm * (mm + 1) / 2;
         }
+        // most edges in a tile of 32 / 16 / 8 consecutive map points (sizes the tiles of the column-slot Schur kernel)
+        for (int p = 0; p < m.P; p += 8) {
+            const int* ob = w->pt_obs_begin;
+            m.tile_edges[2] = std::max(m.tile_edges[2], ob[std::min(p + 8, m.P)] - ob[p]);
+            if (p % 16 == 0) m.tile_edges[1] = std::max(m.tile_edges[1], ob[std::min(p + 16, m.P)] - ob[p]);
+            if (p % 32 == 0) m.tile_edges[0] = std::max(m.tile_edges[0], ob[std::min(p + 32, m.P)] - ob[p]);
+        }
     });
     int max_K = 0, max_nf = 0, max_ni = 0;
     for (int i = 0; i < n_win; ++i) {
@@ -666,6 +698,11 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
             return VILBA_ERR_ARG;
         }
         max_K = std::max(max_K, meta[i].K), max_nf = std::max(max_nf, meta[i].n_free), max_ni = std::max(max_ni, meta[i].NI);
+    }
+    for (int k = 0; k < 3; ++k) {
+        int te = 1;
+        for (int i = 0; i < n_win; ++i) te = std::max(te, meta[i].tile_edges[k]);
+        ctx->tile_edges[k] = (te + 15) / 16 * 16;  // rounded: windows of similar shape share a captured graph
     }
     // shared-memory capacities grow monotonically; the captured graphs depend on them
     if (max_K > ctx->cap_K || max_nf > ctx->cap_nf) {
@@ -756,7 +793,7 @@ bool same_dims(const LaunchDims& a, const LaunchDims& b) {
     return a.sm_count == b.sm_count && a.n_windows == b.n_windows && a.point_grid == b.point_grid && a.imu_grid == b.imu_grid &&
            a.gather_grid == b.gather_grid && a.reduce_grid == b.reduce_grid && a.assemble_grid == b.assemble_grid &&
            a.sp_warps == b.sp_warps && a.sp_sets == b.sp_sets && a.sp_grid == b.sp_grid && a.sp_tile_pts == b.sp_tile_pts &&
-           a.sp_pair_lanes == b.sp_pair_lanes && a.chol_cluster == b.chol_cluster && a.chol_big_tiles == b.chol_big_tiles &&
+           a.sp_pair_lanes == b.sp_pair_lanes && a.sp_mma == b.sp_mma && a.sp_tile_edges == b.sp_tile_edges && a.chol_cluster == b.chol_cluster && a.chol_big_tiles == b.chol_big_tiles &&
            a.chol_nb == b.chol_nb && a.chol_la == b.chol_la && a.chol_n == b.chol_n && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.lin_threads == b.lin_threads && a.smem_chol == b.smem_chol &&
            a.smem_sp == b.smem_sp;
 }
@@ -1104,6 +1141,7 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     if (const char* e = std::getenv("VILBA_SCHUR")) ctx->schur_gather_only = std::strcmp(e, "gather") == 0;
     if (const char* e = std::getenv("VILBA_SP_GRID")) ctx->sp_grid_cap = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_SP_SETS")) ctx->sp_sets = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("VILBA_SP_MMA")) ctx->sp_mma = std::atoi(e) != 0;
     if (const char* e = std::getenv("VILBA_SP_PAIR")) ctx->sp_pair_lanes = std::atoi(e);
     if (const char* e = std::getenv("VILBA_COMM_GRAPH")) ctx->comm_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("VILBA_BATCH_LANES")) ctx->n_lanes = std::max(1, std::atoi(e));

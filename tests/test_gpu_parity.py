@@ -247,6 +247,24 @@ def test_lane_per_pair_schur_variant(oracle, monkeypatch):
         c.close()
 
 
+def test_fp64_mma_schur_variant(oracle, monkeypatch):
+    """The tile kernel that runs every hit as one m8n8k4 FP64 MMA on Z = W G with D^-1 = G G^T (VILBA_SP_MMA=1):
+    single windows, a batch in one launch, extra fixed key-frames, a culled stage 2 and rejected trials."""
+    monkeypatch.setenv("VILBA_SP_MMA", "1")
+    from mc_slam_b200 import api
+    from parity_util import perturbed_window
+    c = api.Context(0)
+    try:
+        for w in (synth.make_config("tiny"), synth.make_config("small", n_fixed_extra=2), synth.make_config("c1", window_index=1),
+                  synth.make_config("c3"), perturbed_window("small", scale=1.0)):
+            _compare(c.local_ba(w), oracle.local_ba(w), w)
+        wins = [synth.make_config("small", window_index=i) for i in range(5)] + [synth.make_config("tiny")]
+        for r, w in zip(c.local_ba_batch(wins), wins):
+            _compare(r, oracle.local_ba(w), w)
+    finally:
+        c.close()
+
+
 def test_rejected_trials_on_the_device(ctx, oracle):
     """Far-off initial estimates make LM reject trials: lambda growth, estimate restore and the stale per-edge chi2 that
     the cull reads must all follow the oracle (and, through tests/test_oracle_vs_dense_lm.py, the dense numpy driver)."""
