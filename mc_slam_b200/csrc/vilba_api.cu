@@ -355,8 +355,10 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
     // every later small one onto the paths for large windows)
     if (!ctx->schur_gather_only && max_K > 0 && schur_tile_fits(max_K, max_nf)) {
         const int max_pairs = max_nf * (max_nf + 1) / 2;
-        d.sp_sets = ctx->sp_sets > 0 ? ctx->sp_sets : (max_pairs >= 40 ? 4 : 1);
         const int max_groups = (max_pairs + 1) / 2;  // a lane group owns two block pairs (a close and a distant one)
+        // CTAs of about 7 warps (35 lane groups): measured best for 19 free key-frames when lanes of a batch overlap
+        // (profiles/r2_schur_variants.md); a single window keeps the finer split, its CTAs have the machine to themselves
+        d.sp_sets = ctx->sp_sets > 0 ? ctx->sp_sets : (n_win > 1 ? std::max(1, (max_groups + 34) / 35) : (max_pairs >= 40 ? 4 : 1));
         d.sp_warps = std::min(16, std::max(1, ((max_groups + d.sp_sets - 1) / d.sp_sets + 4) / 5));
         d.sp_sets = (max_groups + 5 * d.sp_warps - 1) / (5 * d.sp_warps);  // every group must have its lanes
         d.sp_grid = std::max(1, std::min(ctx->sp_grid_cap, 2 * sm / (d.sp_sets * n_win)));
