@@ -15,10 +15,10 @@ extern "C" {
 /* Solve n_windows copies of one dense symmetric system S x = b (S: n x n, full symmetric storage) with a
  * reduced-system kernel of the library (the kernels that replace LinearSolverEigen::solve,
  * g2o/solvers/linear_solver_eigen.h:94-124):
- *   variant 0: cluster kernel, trailing matrix in L2           (chol.cu)
+ *   variant 0: (the round-1 cluster kernel, removed: VILBA_ERR_ARG)
  *   variant 1: look-ahead cluster kernel, trailing matrix in shared memory (chol_la.cu)
- *   variant 2: whole-GPU blocked factorisation                 (chol_big.cu)
- * `cluster` = CTAs per system (variants 0, 1).  The kernel is launched `reps` times (system restored in
+ *   variant 2: multi-kernel blocked factorisation              (chol_big.cu)
+ * `cluster` = CTAs per system (variant 1).  The kernel is launched `reps` times (system restored in
  * between); avg_us receives the mean device time of one launch (CUDA events around the launch only).
  * x_out: n (solution of window 0), fail_out: the kernel's failure flag.  Returns a VILBA_* status. */
 int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S, const double* b, int32_t variant, int32_t cluster,

@@ -1,4 +1,4 @@
-// chol_common.cuh -- device helpers shared by the reduced-system factorisation kernels (chol.cu, chol_la.cu).
+// chol_common.cuh -- device helpers shared by the reduced-system factorisation kernels (chol_la.cu, chol_big.cu).
 #pragma once
 #include <cfloat>
 

@@ -10,8 +10,6 @@
 #include "kernels.h"
 
 namespace vilba {
-cudaError_t configure_chol(const LaunchDims& d);
-cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 }  // namespace vilba
 
 using namespace vilba;
@@ -23,7 +21,7 @@ extern "C" int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S
     if (cudaSetDevice(device) != cudaSuccess) return VILBA_ERR_NO_DEVICE;
     const int ld = (n + 3) & ~3;
     const size_t mat = (size_t)ld * n;
-    const size_t scr = std::max<size_t>(std::max<size_t>(chol_la_scratch_doubles(n), (size_t)256 * (n / 16 + 2)), chol_big_scratch_doubles(n));
+    const size_t scr = std::max<size_t>(chol_la_scratch_doubles(n), chol_big_scratch_doubles(n));
     // per window: S | bs | x | Lfac | cminv | cdinv, then pristine S | b shared by all windows
     const size_t per_win = 2 * mat + 3 * (size_t)ld + scr + 64;  // the last 64: debug counters
     double* dev = nullptr;
@@ -66,7 +64,6 @@ extern "C" int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S
             w.dbg = reinterpret_cast<long long*>(p);
             w.S_w = w.S, w.bs_w = w.bs;
             w.lm = lm + i;
-            w.chol_stage = chol_has_stage(n) ? 1 : 0;
             hlm[i].phase = PH_TRIAL;
         }
         if (cudaMemset(dev, 0, sizeof(double) * (per_win * n_windows)) != cudaSuccess) break;
@@ -80,12 +77,7 @@ extern "C" int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S
         d.n_windows = n_windows;
         d.chol_cluster = cluster;
         cudaError_t e = cudaSuccess;
-        if (variant == 0) {
-            d.chol_nb = chol_block_size(n);
-            d.smem_chol = chol_smem_bytes(n);
-            if (d.smem_chol > 227 * 1024) { status = VILBA_ERR_ARG; break; }
-            e = configure_chol(d);
-        } else if (variant == 1) {
+        if (variant == 1) {
             if (!chol_la_fits(n, cluster)) { status = VILBA_ERR_ARG; break; }
             e = configure_chol_la();
         } else if (variant == 2) {
@@ -104,8 +96,7 @@ extern "C" int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S
             }
             if (!ok) break;
             cudaEventRecord(e0, s);
-            if (variant == 0) e = launch_chol_cluster(s, dwp, d);
-            else if (variant == 1) e = launch_chol_la(s, dwp, n_windows, cluster, n);
+            if (variant == 1) e = launch_chol_la(s, dwp, n_windows, cluster, n);
             else e = launch_chol_big(s, side, ef, ej, dwp, d);
             cudaEventRecord(e1, s);
             if (e != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { ok = false; break; }
@@ -149,7 +140,6 @@ extern "C" int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S
 
 extern "C" int vilba_diag_dense_supported(int32_t n, int32_t variant, int32_t cluster) {
     if (n < 1 || cluster < 1) return 0;
-    if (variant == 0) return chol_smem_bytes(n) <= 227 * 1024 && cluster <= 16;
     if (variant == 1) return chol_la_fits(n, cluster) && cluster <= 16;
     return variant == 2;
 }

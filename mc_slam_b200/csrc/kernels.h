@@ -138,7 +138,6 @@ struct DevWindow {
     unsigned* chi_counter;   // CTAs of update_eval that have delivered their partial
     long long* dbg;  // optional debug counters (16 x int64), may be null
     int dbg_flags;   // timing-ablation switches (only honoured by -DVILBA_CHOL_TIMING builds)
-    int chol_stage;  // 1 if the Cholesky launch carries the shared-memory row stage of the back substitution
     // calibration (g2otypes.h:686-705)
     double fx, fy, cx, cy;
     double Rcb[9];  // Rbc^T
@@ -199,17 +198,14 @@ struct LaunchDims {
     int chol_cluster;     // CTAs of the Cholesky cluster
     int chol_la;          // 1: look-ahead cluster kernel with the trailing matrix in shared memory (chol_la.cu)
     int chol_n;           // largest reduced system of the batch (sizes the shared memory of chol_la)
-    int chol_big_tiles;   // > 0: whole-GPU blocked Cholesky (chol_big.cu) with this many 64-column steps, instead of the cluster kernel
-    int chol_nb;          // columns per Cholesky step: 32 while the panel fits in shared memory, else 16
+    int chol_big_tiles;   // > 0: multi-kernel blocked LDL^T (chol_big.cu) with this many 64-column steps (systems too large for chol_la)
     size_t smem_point;    // dynamic shared memory of update_eval / flags
     size_t smem_lin;      // ... of linearize_v2
     int lin_threads;      // threads per CTA of linearize_v2: fewer warps (= fewer private accumulators) for many free key-frames
-    size_t smem_chol;     // ... of chol_cluster
     size_t smem_sp;       // ... of schur_tile
 };
 size_t point_smem_bytes(int K);
 size_t linearize_smem_bytes(int K, int n_free, int threads);
-size_t chol_smem_bytes(int n);
 bool schur_tile_fits(int K, int n_free);   // the tile-scan Schur kernel handles windows of <= 32 key-frames
 size_t schur_tile_smem_bytes(int max_K, int tile_pts);
 size_t schur_tile_rec_doubles(int P);
@@ -219,8 +215,6 @@ int schur_pair_lanes(int n_free);                 // lanes (= threads) of the la
 size_t schur_pair_partial_doubles(int n_free);    // size of one of its partial sums
 size_t schur_tile_hdr_words(int P, int tile_pts);
 size_t schur_partial_doubles(int n_free);
-bool chol_has_stage(int n_cap);
-int chol_block_size(int n_cap);
 cudaError_t configure_chol_big(int n_cap);
 size_t chol_big_scratch_doubles(int n);  // DevWindow::cminv must hold this many doubles when chol_big.cu is used
 // look-ahead cluster kernel with the trailing matrix in shared memory (chol_la.cu)

@@ -9,7 +9,7 @@
 //                 and the iteration loop of SparseOptimizer::optimize (sparse_optimizer.cpp:376-414), kept in
 //                 device memory so that the host never synchronises inside an optimize() call
 //   flags       : the cull / outlier loops of Optimizer::LocalBundleAdjustmentNavState (Optimizer.cpp:2659-2701)
-// The accumulation kernels (linearize / assemble / Schur) live in lba_v2.cu, the Cholesky in chol.cu.
+// The accumulation kernels (linearize / assemble / Schur) live in lba_v2.cu, the reduced-system LDL^T in chol_la.cu / chol_big.cu.
 //
 // Work decomposition: eight lanes per map point (its mono edges sit on the lanes), one lane group per
 // IMU edge pair; every CTA first stages the key-frame states it needs (camera rotation

@@ -1221,9 +1221,7 @@ cudaError_t launch_lm_iter_begin(cudaStream_t s, const DevWindow* wp, const Laun
 cudaError_t launch_lm_decide(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_shard_diag(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_shard_scale(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
-cudaError_t launch_chol_cluster(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t configure_point_kernels(const LaunchDims& d);
-cudaError_t configure_chol(const LaunchDims& d);
 
 cudaError_t configure_kernels(const LaunchDims& d) {
     cudaError_t e = opt_in_max_smem(linearize_v2_kernel);
@@ -1238,7 +1236,7 @@ cudaError_t configure_kernels(const LaunchDims& d) {
     if (e != cudaSuccess) return e;
     if ((e = configure_chol_big(0)) != cudaSuccess) return e;
     if ((e = configure_chol_la()) != cudaSuccess) return e;
-    return configure_chol(d);
+    return cudaSuccess;
 }
 
 cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, const DevWindow* wp,
@@ -1285,8 +1283,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     if (comm && (e = comm->reduce(comm->self, RED_S, s)) != cudaSuccess) return e;  // S | b_s = sum of the partial reduced systems
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
     if (d.chol_big_tiles > 0) e = launch_chol_big(s, side, fork, join, wp, d);
-    else if (d.chol_la) e = launch_chol_la(s, wp, d.n_windows, d.chol_cluster, d.chol_n);
-    else e = launch_chol_cluster(s, wp, d);
+    else e = launch_chol_la(s, wp, d.n_windows, d.chol_cluster, d.chol_n);
     if (e != cudaSuccess) return e;
     if (probe && (e = cudaEventRecord(probe[4], s)) != cudaSuccess) return e;
     if ((e = launch_update_eval_apply(s, wp, d)) != cudaSuccess) return e;

@@ -3,7 +3,7 @@
 // The host side mirrors the control flow of Optimizer::LocalBundleAdjustmentNavState phases C..E
 // (src/Optimizer.cpp:2643-2701) and of SparseOptimizer::optimize / OptimizationAlgorithmLevenberg::solve
 // (g2o/core/sparse_optimizer.cpp:354-419, optimization_algorithm_levenberg.cpp:61-164); all arithmetic
-// runs in the CUDA kernels of lba_kernels.cu / lba_v2.cu / chol.cu / preint.cu.  There is no CPU fallback:
+// runs in the CUDA kernels of lba_kernels.cu / lba_v2.cu / chol_la.cu / chol_big.cu / preint.cu.  There is no CPU fallback:
 // without a usable CUDA device vilba_create() returns NULL.
 //
 // A context holds a *batch* of 1..kMaxBatch independent windows.  Every kernel is launched once for the
@@ -151,8 +151,7 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bo
     L.bs = take(sizeof(double) * n);  // directly behind S: one allreduce covers S | b_s of a sharded window
     L.s_span = L.bs + sizeof(double) * n - L.S;
     L.Lfac = take(sizeof(double) * lds * n);
-    L.cminv = take(sizeof(double) * std::max<size_t>(std::max<size_t>(256 * (n / 16 + 2), chol_la_scratch_doubles((int)n)),
-                                                     chol_big_scratch_doubles((int)n)));
+    L.cminv = take(sizeof(double) * std::max<size_t>(chol_la_scratch_doubles((int)n), chol_big_scratch_doubles((int)n)));
     L.cdinv = take(sizeof(double) * n);
     L.x = take(sizeof(double) * n);
     L.dbg = take(sizeof(long long) * 16);
@@ -239,9 +238,9 @@ bool fail(vilba_ctx* c, cudaError_t e, const char* what) {
     if (e == cudaSuccess) return false;
     const LaunchDims& d = c->dims;
     char geo[256];
-    std::snprintf(geo, sizeof(geo), " [windows %d, grids %d/%d/%d/%d/%d, schur %d warps x %d sets x %d, chol %d (big %d), smem %zu/%zu/%zu/%zu]",
+    std::snprintf(geo, sizeof(geo), " [windows %d, grids %d/%d/%d/%d/%d, schur %d warps x %d sets x %d, chol %d (big %d), smem %zu/%zu/%zu]",
                   d.n_windows, d.point_grid, d.imu_grid, d.gather_grid, d.reduce_grid, d.assemble_grid, d.sp_warps, d.sp_sets, d.sp_grid,
-                  d.chol_cluster, d.chol_big_tiles, d.smem_point, d.smem_lin, d.smem_chol, d.smem_sp);
+                  d.chol_cluster, d.chol_big_tiles, d.smem_point, d.smem_lin, d.smem_sp);
     c->err = std::string(what) + ": " + cudaGetErrorString(e) + geo;
     return true;
 }
@@ -396,30 +395,23 @@ LaunchDims choose_dims(const vilba_ctx* ctx, int n_win, int max_ni, int max_K, i
             }
         }
     }
-    // Cholesky.  Large reduced systems: blocked factorisation over the whole GPU (chol_big.cu); small ones: one cluster
-    // per window, as many CTAs as the machine has to spare (one 8-CTA cluster for a single window, smaller clusters when
-    // many windows share the SMs: a CTA is more efficient the fewer partners it waits for)
+    // Reduced system.  chol_la.cu (one cluster per window, the trailing matrix in the shared memory of the cluster) takes
+    // every system that fits (n <= 345 with 8 CTAs; n = 285 needs 4, n = 135 one): the full cluster for one window
+    // (latency), the smallest cluster that fits for a batch (the windows of all lanes share the SMs).  Larger systems, or
+    // env VILBA_CHOL_LA=0: the multi-kernel blocked factorisation of chol_big.cu.  Both are LDL^T with the failure rule of
+    // Eigen's SimplicialLDLT (a zero or non-finite pivot fails the trial, a negative one does not).
     const int n_cur = 15 * max_nf;
-    d.chol_big_tiles = (n_cur > ctx->chol_big_above) ? (n_cur + 63) / 64 : 0;
-    d.chol_nb = chol_block_size(n_cur);
-    if (const char* e = std::getenv("VILBA_CHOL_NB")) d.chol_nb = (std::atoi(e) == 16) ? 16 : d.chol_nb;
-    d.smem_chol = d.chol_big_tiles > 0 ? 0 : chol_smem_bytes(n_cur);
-    int cl = 1;
-    const int n_all = std::max(n_win, ctx->batch_total_hint);  // windows of all concurrent lanes share the SMs
-    while (2 * cl <= ctx->chol_cluster && 2 * cl * n_all <= sm) cl *= 2;
-    d.chol_cluster = n_win == 1 ? ctx->chol_cluster : cl;
-    // the look-ahead kernel (chol_la.cu) keeps the trailing matrix in the shared memory of the cluster: it needs enough
-    // CTAs per window for the tiles to fit (n = 285: 4, n = 135: 1).  One window: the full cluster (latency).  A batch:
-    // the smallest cluster that fits, as long as all windows of all lanes still find room on the machine
-    d.chol_la = 0;
-    d.chol_n = 15 * max_nf;
-    if (ctx->chol_la_mode != 0 && d.chol_big_tiles == 0 && max_nf > 0) {
+    d.chol_n = n_cur;
+    d.chol_la = 0, d.chol_big_tiles = 0;
+    d.chol_cluster = ctx->chol_cluster;
+    if (max_nf > 0) {
         int c = n_win == 1 ? ctx->chol_cluster : 1;
-        while (c <= 8 && !chol_la_fits(d.chol_n, c)) c *= 2;
-        const bool room = n_win == 1 || ctx->chol_la_mode == 2 || c * n_all <= 2 * sm;
-        if (c <= std::max(8, ctx->chol_cluster) && chol_la_fits(d.chol_n, c) && room) {
+        while (c < 8 && !chol_la_fits(n_cur, c)) c *= 2;
+        if (ctx->chol_la_mode != 0 && n_cur <= ctx->chol_big_above && chol_la_fits(n_cur, c)) {
             d.chol_la = 1;
             d.chol_cluster = c;
+        } else {
+            d.chol_big_tiles = (n_cur + 63) / 64;
         }
     }
     return d;
@@ -749,7 +741,6 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     LmState* lm0 = reinterpret_cast<LmState*>(d + ctx->lm_base);
     for (int i = 0; i < n_win; ++i) {
         fill_dev_window(ctx, &wins[i], meta[i], d, lm0 + i, ctx->dw[i]);
-        ctx->dw[i].chol_stage = chol_has_stage(15 * max_nf) ? 1 : 0;
     }
     std::memcpy(ctx->pinned_small.base, ctx->dw.data(), sizeof(DevWindow) * (size_t)n_win);
     CK(cudaMemcpyAsync(ctx->dwp, ctx->pinned_small.base, sizeof(DevWindow) * (size_t)n_win, cudaMemcpyHostToDevice,
@@ -796,7 +787,7 @@ bool same_dims(const LaunchDims& a, const LaunchDims& b) {
            a.gather_grid == b.gather_grid && a.reduce_grid == b.reduce_grid && a.assemble_grid == b.assemble_grid &&
            a.sp_warps == b.sp_warps && a.sp_sets == b.sp_sets && a.sp_grid == b.sp_grid && a.sp_tile_pts == b.sp_tile_pts &&
            a.sp_pair_lanes == b.sp_pair_lanes && a.sp_mma == b.sp_mma && a.sp_tile_edges == b.sp_tile_edges && a.chol_cluster == b.chol_cluster && a.chol_big_tiles == b.chol_big_tiles &&
-           a.chol_nb == b.chol_nb && a.chol_la == b.chol_la && a.chol_n == b.chol_n && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.lin_threads == b.lin_threads && a.smem_chol == b.smem_chol &&
+           a.chol_la == b.chol_la && a.chol_n == b.chol_n && a.smem_point == b.smem_point && a.smem_lin == b.smem_lin && a.lin_threads == b.lin_threads &&
            a.smem_sp == b.smem_sp;
 }
 
@@ -1134,7 +1125,6 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     std::memset(&ctx->dims, 0, sizeof(ctx->dims));
-    ctx->dims.chol_nb = 32;
     if (const char* e = std::getenv("VILBA_CHOL_CLUSTER")) ctx->chol_cluster = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VILBA_GRAPH")) ctx->use_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("VILBA_CHOL_BIG_ABOVE")) ctx->chol_big_above = std::atoi(e);

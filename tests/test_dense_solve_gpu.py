@@ -37,14 +37,13 @@ def test_lookahead_cluster_kernel_matches_numpy(n, cluster):
     assert lib is not None
 
 
-@pytest.mark.parametrize("n,cluster", [(135, 8), (285, 8), (285, 2), (405, 8), (465, 8)])
-def test_old_cluster_kernel_matches_numpy(n, cluster):
-    S, b = spd(n, 200 + n)
-    x, fail, _ = capi.diag_dense_solve(S, b, variant=0, cluster=cluster)
-    assert fail == 0 and rel_err(S, b, x) < 1e-7
+def test_removed_variant_is_rejected():
+    S, b = spd(30, 5)
+    with pytest.raises(Exception):
+        capi.diag_dense_solve(S, b, variant=0, cluster=1)
 
 
-@pytest.mark.parametrize("n", [495, 1000, 1485])
+@pytest.mark.parametrize("n", [15, 100, 360, 405, 465, 480, 495, 1000, 1485])  # 345 < n <= 480: beyond chol_la in the product
 def test_whole_gpu_kernel_matches_numpy(n):
     S, b = spd(n, 300 + n, cond=1e6)
     x, fail, _ = capi.diag_dense_solve(S, b, variant=2, cluster=1)

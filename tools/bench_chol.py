@@ -1,7 +1,6 @@
 #!/usr/bin/env python
-"""Times the reduced-system kernels alone (include/vilba_diag.h) on S-like SPD systems: variant 0 = cluster kernel with
-the trailing matrix in L2 (chol.cu), 1 = look-ahead cluster kernel with shared-memory tiles (chol_la.cu), 2 = whole-GPU
-blocked factorisation (chol_big.cu).  Usage: bench_chol.py [n,n,...] [reps]"""
+"""Times the reduced-system kernels alone (include/vilba_diag.h) on S-like SPD systems: variant 1 = look-ahead cluster
+kernel with shared-memory tiles (chol_la.cu), 2 = multi-kernel blocked factorisation (chol_big.cu).  Usage: bench_chol.py [n,n,...] [reps]"""
 import os
 import sys
 
@@ -19,7 +18,7 @@ for n in sizes:
     S = 0.5 * (S + S.T)
     b = rng.standard_normal(n)
     ref = np.linalg.solve(S, b)
-    for variant, clusters in ((0, (1, 2, 8)), (1, (1, 2, 4, 8, 16)), (2, (1,))):
+    for variant, clusters in ((1, (1, 2, 4, 8, 16)), (2, (1,))):
         for cl in clusters:
             for nw in (1, 16, 64):
                 if variant == 2 and (nw > 1 or n < 300):
