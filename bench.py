@@ -156,13 +156,14 @@ def ncu_traffic(kernel, nw, workload):
         return None
 
 
-def cpu_throughput(wins, threads, reps_per_thread):
+def cpu_throughput(wins, threads, reps_per_thread, warm=True):
     """The CPU restatement of the reference path (oracle/, g++ -O3 -march=native) on `threads` host threads,
     one window per thread at a time (g2o itself is single-threaded per optimisation: Thirdparty/g2o/config.h:4).
     Returns (LM iters/s over the wall time of the sample, windows solved, iters, edges, wall seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle
-    pyoracle.local_ba(wins[0])  # warm-up (library load, page-in)
+    if warm:
+        pyoracle.local_ba(wins[0])  # warm-up (library load, page-in)
     jobs = [wins[i % len(wins)] for i in range(threads * reps_per_thread)]
 
     def one(w):
@@ -564,6 +565,20 @@ def main():
                 single["cpu_single_thread"] = v1
                 single["ratio_vs_cpu_single_thread"] = single["value"] / v1
                 single["e2e_ratio_vs_cpu_single_thread"] = single["e2e"] / v1
+            # configs 1, 2 and 4 next to ONE host core running the restatement (C4: one solve of ~10 s)
+            for name, reps_ in (("c1", 3), ("c4", 1)):
+                if name in line:
+                    vc, _, _, _, _ = cpu_throughput([synth.make_config(name)], 1, reps_, warm=name != "c4")
+                    line[name]["cpu_single_thread"] = vc
+                    line[name]["ratio_vs_cpu_single_thread"] = line[name]["value"] / vc
+            if "c2_preint" in line:
+                from oracle import pyoracle  # (the CPU baseline leg is where bench.py may execute oracle/)
+                b2 = synth.make_imu_batch(n_pairs=512, n_samples=40)
+                pyoracle.preintegrate_batch(b2.sample_begin, b2.gyro, b2.acc, b2.dt, b2.bg, b2.ba)
+                t0 = time.perf_counter()
+                pyoracle.preintegrate_batch(b2.sample_begin, b2.gyro, b2.acc, b2.dt, b2.bg, b2.ba)
+                line["c2_preint"]["cpu_single_thread_pairs_per_sec"] = 512 / (time.perf_counter() - t0)
+                line["c2_preint"]["cpu_sample"] = "512 of the 4096 pairs, one host thread, oracle restatement"
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -69,7 +69,8 @@ struct DevWindow {
     double* pts[2];       // P * 3
     const double* kf_state0;  // uploaded initial estimates (every solve restarts from them)
     const double* pts0;
-    const int4* obs0;
+    const char* obs0;        // E x 16 B as uploaded: uv (2 f32 per edge) | inv sigma^2 (f32) | key-frame index (i32)
+    int obs_flags0;          // flag bits every edge record starts a solve with (OBS_ROBUST or 0)
     uint8_t* outlier;     // E: final outlier flags
     // packed results of this window inside the batch's output region (one D2H for the whole batch)
     double* out_kf_state;

@@ -412,8 +412,13 @@ __global__ void __launch_bounds__(256) reset_kernel(const DevWindow* __restrict_
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (int i = tid; i < 22 * w.K; i += nt) w.kf_state[0][i] = w.kf_state[1][i] = w.kf_state0[i];
     for (int i = tid; i < 3 * w.P; i += nt) w.pts[0][i] = w.pts[1][i] = w.pts0[i];
+    // the edge records {u, v, inv sigma^2 as f32 bits, key-frame index | flags} from the three uploaded arrays
+    const int2* uv = reinterpret_cast<const int2*>(w.obs0);
+    const int* is2 = reinterpret_cast<const int*>(w.obs0 + 8 * (size_t)w.E);
+    const int* kf = reinterpret_cast<const int*>(w.obs0 + 12 * (size_t)w.E);
     for (int i = tid; i < w.E; i += nt) {
-        w.obs[i] = w.obs0[i];
+        const int2 p = uv[i];
+        w.obs[i] = make_int4(p.x, p.y, is2[i], kf[i] | w.obs_flags0);
         w.obs_chi2[i] = 0.0;
     }
     int* lm = reinterpret_cast<int*>(w.lm);

@@ -424,20 +424,19 @@ void drop_graphs(vilba_ctx* ctx) {
 
 // flatten one window into its slice of the pinned staging buffer (phase A/B of the reference function:
 // gather + graph build, Optimizer.cpp:2329-2639, become "pack + one H2D")
-void pack_window(const vilba_window* w, const WinMeta& m, char* h, int mono_flags) {
+void pack_window(const vilba_window* w, const WinMeta& m, char* h) {
     const Layout& L = m.L;
     const int K = m.K, NI = m.NI, P = m.P, E = m.E, n_free = m.n_free, n_pairs = m.n_pairs;
     std::memcpy(h + L.kf_state0, w->kf_state, sizeof(double) * 22 * (size_t)K);
     if (P) std::memcpy(h + L.pts0, w->pt_xyz, sizeof(double) * 3 * (size_t)P);
     if (NI) std::memcpy(h + L.imu_preint, w->imu_preint, sizeof(double) * 142 * (size_t)NI);
-    int4* ho = reinterpret_cast<int4*>(h + L.obs0);
-    for (int e = 0; e < E; ++e) {
-        int4 r;
-        std::memcpy(&r.x, &w->obs_uv[2 * (size_t)e], 4);
-        std::memcpy(&r.y, &w->obs_uv[2 * (size_t)e + 1], 4);
-        std::memcpy(&r.z, &w->obs_inv_sigma2[e], 4);
-        r.w = w->obs_kf[e] | mono_flags;  // OBS_ROBUST: the edge starts with its Huber kernel (Optimizer.cpp:2622-2624)
-        ho[e] = r;
+    // the observations travel as the caller's three arrays (plain copies: the host threads of 8 processes x 4 lanes share
+    // the cores); reset_kernel interleaves them into the 16-byte edge records at the start of every solve
+    if (E) {
+        char* ho = h + L.obs0;
+        std::memcpy(ho, w->obs_uv, 8 * (size_t)E);
+        std::memcpy(ho + 8 * (size_t)E, w->obs_inv_sigma2, 4 * (size_t)E);
+        std::memcpy(ho + 12 * (size_t)E, w->obs_kf, 4 * (size_t)E);
     }
     if (P) std::memcpy(h + L.pt_obs_begin, w->pt_obs_begin, sizeof(int) * ((size_t)P + 1));
     else std::memset(h + L.pt_obs_begin, 0, sizeof(int));
@@ -483,7 +482,9 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     }
     dw.kf_state0 = reinterpret_cast<const double*>(in + L.kf_state0);
     dw.pts0 = reinterpret_cast<const double*>(in + L.pts0);
-    dw.obs0 = reinterpret_cast<const int4*>(in + L.obs0);
+    dw.obs0 = in + L.obs0;
+    // every mono edge starts with its Huber kernel (Optimizer.cpp:2622-2624) unless bRobust is false (:1590-1595)
+    dw.obs_flags0 = (ctx->prm.mode & VILBA_MODE_MONO_NOT_ROBUST) ? 0 : OBS_ROBUST;
     dw.outlier = reinterpret_cast<uint8_t*>(wk + L.outlier);
     dw.out_kf_state = reinterpret_cast<double*>(out + L.o_kf);
     dw.out_pts = reinterpret_cast<double*>(out + L.o_pts);
@@ -730,8 +731,7 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     CK(ctx->pinned_small.reserve(sizeof(DevWindow) * (size_t)n_win + 256), "cudaMallocHost(desc)");
     char* h = ctx->pinned.base;
     char* d = ctx->arena.base;
-    const int mono_flags = (ctx->prm.mode & VILBA_MODE_MONO_NOT_ROBUST) ? 0 : OBS_ROBUST;
-    parallel_for(n_win, host_threads, [&](int i) { pack_window(&wins[i], meta[i], h + meta[i].in_base, mono_flags); });
+    parallel_for(n_win, host_threads, [&](int i) { pack_window(&wins[i], meta[i], h + meta[i].in_base); });
     const auto t_packed = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(d, h, in_o, cudaMemcpyHostToDevice, ctx->stream), "H2D windows");
     if (std::getenv("VILBA_DEBUG_COUNTERS"))
@@ -1115,6 +1115,19 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
         return nullptr;
     }
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    {
+        // How host threads wait for the device.  Spinning is the fastest wake-up but holds a core; with one process per
+        // GPU and one thread per lane a node can have as many waiting threads as cores (8 x 4 on 32), and the threads
+        // that flatten / scatter windows then have none: yield instead.  env VILBA_SYNC = spin | yield | block.
+        static const int procs = std::getenv("LOCAL_WORLD_SIZE") ? std::max(1, std::atoi(std::getenv("LOCAL_WORLD_SIZE"))) : 1;
+        const char* e = std::getenv("VILBA_SYNC");
+        const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+        unsigned flag = (procs * 4 * 2 > hw) ? cudaDeviceScheduleYield : cudaDeviceScheduleAuto;
+        if (e && !std::strcmp(e, "spin")) flag = cudaDeviceScheduleSpin;
+        if (e && !std::strcmp(e, "yield")) flag = cudaDeviceScheduleYield;
+        if (e && !std::strcmp(e, "block")) flag = cudaDeviceScheduleBlockingSync;
+        if (flag != cudaDeviceScheduleAuto && cudaSetDeviceFlags(flag) != cudaSuccess) cudaGetLastError();  // not fatal
+    }
     vilba_ctx* ctx = new vilba_ctx();
     ctx->device = device;
     if (params)
