@@ -1115,19 +1115,6 @@ vilba_ctx* vilba_create(int device, const vilba_params* params) {
         return nullptr;
     }
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
-    {
-        // How host threads wait for the device.  Spinning is the fastest wake-up but holds a core; with one process per
-        // GPU and one thread per lane a node can have as many waiting threads as cores (8 x 4 on 32), and the threads
-        // that flatten / scatter windows then have none: yield instead.  env VILBA_SYNC = spin | yield | block.
-        static const int procs = std::getenv("LOCAL_WORLD_SIZE") ? std::max(1, std::atoi(std::getenv("LOCAL_WORLD_SIZE"))) : 1;
-        const char* e = std::getenv("VILBA_SYNC");
-        const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-        unsigned flag = (procs * 4 * 2 > hw) ? cudaDeviceScheduleYield : cudaDeviceScheduleAuto;
-        if (e && !std::strcmp(e, "spin")) flag = cudaDeviceScheduleSpin;
-        if (e && !std::strcmp(e, "yield")) flag = cudaDeviceScheduleYield;
-        if (e && !std::strcmp(e, "block")) flag = cudaDeviceScheduleBlockingSync;
-        if (flag != cudaDeviceScheduleAuto && cudaSetDeviceFlags(flag) != cudaSuccess) cudaGetLastError();  // not fatal
-    }
     vilba_ctx* ctx = new vilba_ctx();
     ctx->device = device;
     if (params)
