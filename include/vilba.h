@@ -55,6 +55,11 @@ extern "C" {
 #define VILBA_PI_COV 60
 #define VILBA_PI_DT 141
 
+/* Key-frames per window, free and fixed together: their states are staged in shared memory by every per-point
+ * kernel (the reference has no limit; its local windows hold 10-20 local and a few dozen fixed key-frames, a global
+ * BA over a longer map has to be cut or sharded).  Larger windows are rejected with VILBA_ERR_ARG. */
+#define VILBA_MAX_KEYFRAMES 256
+
 /* key-frame flags */
 #define VILBA_KF_FIXED 1u      /* VertexNavStatePVR::setFixed(true)   (src/Optimizer.cpp:2454-2467)        */
 #define VILBA_KF_HAS_BIAS 2u   /* a VertexNavStateBias exists for it  (src/Optimizer.cpp:2435-2443,2470-2478) */
@@ -111,7 +116,7 @@ void vilba_default_params(vilba_params* p);
  * ------------------------------------------------------------------------------------------- */
 typedef struct vilba_window {
     /* key-frames */
-    int32_t n_kf;
+    int32_t n_kf;                  /* <= VILBA_MAX_KEYFRAMES (fixed ones included)                         */
     int32_t n_imu;                 /* number of (EdgeNavStatePVR, EdgeNavStateBias) pairs                  */
     int32_t n_pts;
     int32_t n_obs;                 /* number of EdgeNavStatePVRPointXYZ                                    */

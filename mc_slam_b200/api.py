@@ -105,9 +105,10 @@ class Context:
         return res
 
     # ---- the same two calls with caller-owned, reusable buffers (what a C++ caller does) -----------
-    def prepare(self, wins: Sequence[Window]) -> "PreparedBatch":
-        """Allocates the result arrays and the ctypes views of `wins` once; run() is then only the C-ABI call."""
-        return PreparedBatch(self, list(wins))
+    def prepare(self, wins: Sequence[Window], chi2: bool = True) -> "PreparedBatch":
+        """Allocates the result arrays and the ctypes views of `wins` once; run() is then only the C-ABI call.
+        `chi2=False` asks for what the reference's function returns (states, points, outlier flags) and no per-edge chi2."""
+        return PreparedBatch(self, list(wins), chi2)
 
     # ---- resident batch of independent windows (one batched launch per kernel) --------------------
     def upload_batch(self, wins: Sequence[Window]):
@@ -184,12 +185,14 @@ class PreparedBatch:
     """Host buffers of a batch, owned by the caller and reused across calls: the inputs as ctypes views of the
     numpy arrays, the outputs pre-allocated.  run() = vilba_local_ba_batch (or vilba_local_ba for one window)."""
 
-    def __init__(self, ctx: Context, wins: List[Window]):
+    def __init__(self, ctx: Context, wins: List[Window], chi2: bool = True):
         self.ctx, self.wins = ctx, wins
         n = len(wins)
-        self.results = [Result.alloc(w) for w in wins]
+        self.results = [Result.alloc(w, chi2) for w in wins]
         for r in self.results:  # touch the pages now: the first write is otherwise paid inside the call
-            r.kf_state.fill(0), r.pt_xyz.fill(0), r.obs_outlier.fill(0), r.obs_chi2.fill(0)
+            r.kf_state.fill(0), r.pt_xyz.fill(0), r.obs_outlier.fill(0)
+            if r.obs_chi2 is not None:
+                r.obs_chi2.fill(0)
         self._cws = (CWindow * n)(*[w.as_c() for w in wins])
         self._crs = (CResult * n)(*[r.as_c() for r in self.results])
 

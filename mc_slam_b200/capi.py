@@ -302,7 +302,7 @@ class Result:
     kf_state: np.ndarray
     pt_xyz: np.ndarray
     obs_outlier: np.ndarray
-    obs_chi2: np.ndarray
+    obs_chi2: Optional[np.ndarray]
     status: int = 0
     stage2_ran: int = 0
     n_outliers_stage1: int = 0
@@ -310,12 +310,14 @@ class Result:
     solve_ms: float = 0.0
 
     @staticmethod
-    def alloc(win: Window) -> "Result":
+    def alloc(win: Window, chi2: bool = True) -> "Result":
+        """`chi2=False`: no per-edge chi2 array (the reference's function does not hand one back either); the library
+        then leaves that part of the results on the device."""
         return Result(
             kf_state=np.zeros((win.n_kf, NS_DOUBLES), np.float64),
             pt_xyz=np.zeros((win.n_pts, 3), np.float64),
             obs_outlier=np.zeros((win.n_obs,), np.uint8),
-            obs_chi2=np.zeros((win.n_obs,), np.float64),
+            obs_chi2=np.zeros((win.n_obs,), np.float64) if chi2 else None,
         )
 
     def as_c(self) -> CResult:

@@ -76,7 +76,8 @@ struct Layout {
     size_t kf_state0, pts0, imu_preint, obs0, pt_obs_begin, kf_block, imu_i, imu_j, blk_edge_i, blk_edge_j, blk_kf,
         pair_a, pair_b, in_bytes;
     // output region (all windows contiguous => one D2H copy per batch); offsets relative to out_base
-    size_t o_kf, o_pts, o_chi2, o_outlier, out_bytes;
+    size_t o_kf, o_pts, o_outlier, out_bytes;
+    size_t chi_bytes;  // per-edge chi2 lives in a second region behind the outputs of all windows: copied only on request
     // work region; offsets relative to wk_base
     size_t edge_pt, pair_begin, pair_ea, pair_eb, pt_mask;
     size_t kf_state[2], pts[2], imu_info, imu_err, obs, obs_chi2, Hpp, bp, Hll, bl, W, lin_partial, imu_slot, mono_sum, Y,
@@ -88,7 +89,7 @@ struct WinMeta {
     size_t n_triples = 0;
     int tile_edges[3] = {0, 0, 0};  // most edges in a tile of 32 / 16 / 8 map points
     Layout L;
-    size_t in_base = 0, out_base = 0, wk_base = 0;
+    size_t in_base = 0, out_base = 0, chi_base = 0, wk_base = 0;
 };
 
 Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bool sharded) {
@@ -118,9 +119,11 @@ Layout make_layout(const WinMeta& m, int lin_ctas, int sp_ctas, int tile_pts, bo
     o = 0;
     L.o_kf = take(sizeof(double) * 22 * K);
     L.o_pts = take(sizeof(double) * 3 * P);
-    L.o_chi2 = take(sizeof(double) * E);
     L.o_outlier = take(E);
     L.out_bytes = o;
+    o = 0;
+    take(sizeof(double) * E);
+    L.chi_bytes = o;
     o = 0;
     L.edge_pt = take(sizeof(int) * E);
     L.pair_begin = take(sizeof(int) * (n_pairs + 1));
@@ -187,7 +190,7 @@ struct vilba_ctx {
     std::vector<WinMeta> meta;
     std::vector<DevWindow> dw;  // host copies
     DevWindow* dwp = nullptr;   // device array the kernels read (fixed address => graph-capturable launches)
-    size_t in_total = 0, out_total = 0, lm_base = 0, out_region = 0;  // arena: [in | out | lm array | work]
+    size_t in_total = 0, out_total = 0, out_small = 0, lm_base = 0, out_region = 0;  // arena: [in | out | chi2 | lm array | work]
     LaunchDims dims;
     int chol_cluster = 8;
     int preint_group = 0;            // env VILBA_PREINT_GROUP: 0 = scan kernel, lanes per pair chosen from the average interval length;
@@ -252,7 +255,7 @@ bool fail(vilba_ctx* c, cudaError_t e, const char* what) {
 
 int check_window(const vilba_window* w) {
     if (!w || w->n_kf <= 0 || w->n_imu < 0 || w->n_pts < 0 || w->n_obs < 0) return VILBA_ERR_ARG;
-    if (w->n_kf > (OBS_KF_MASK) || w->n_kf > kMaxKF) return VILBA_ERR_ARG;
+    if (w->n_kf > (OBS_KF_MASK) || w->n_kf > kMaxKF) return VILBA_ERR_ARG - 200;  // (reported as "too many key-frames")
     if (!w->kf_state || !w->kf_flags) return VILBA_ERR_ARG;
     if (w->n_imu && (!w->imu_kf_i || !w->imu_kf_j || !w->imu_preint)) return VILBA_ERR_ARG;
     if (w->n_pts && (!w->pt_xyz || !w->pt_obs_begin)) return VILBA_ERR_ARG;
@@ -488,7 +491,7 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.outlier = reinterpret_cast<uint8_t*>(wk + L.outlier);
     dw.out_kf_state = reinterpret_cast<double*>(out + L.o_kf);
     dw.out_pts = reinterpret_cast<double*>(out + L.o_pts);
-    dw.out_chi2 = reinterpret_cast<double*>(out + L.o_chi2);
+    dw.out_chi2 = reinterpret_cast<double*>(d + m.chi_base);
     dw.out_outlier = reinterpret_cast<uint8_t*>(out + L.o_outlier);
     dw.kf_block = reinterpret_cast<const int*>(in + L.kf_block);
     dw.imu_i = reinterpret_cast<const int*>(in + L.imu_i);
@@ -689,7 +692,9 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     int max_K = 0, max_nf = 0, max_ni = 0;
     for (int i = 0; i < n_win; ++i) {
         if (status[i] != VILBA_OK) {
-            ctx->err = status[i] == VILBA_ERR_ARG - 100 ? "a key-frame may start / end at most one IMU edge" : "invalid window";
+            ctx->err = status[i] == VILBA_ERR_ARG - 100   ? "a key-frame may start / end at most one IMU edge"
+                       : status[i] == VILBA_ERR_ARG - 200 ? "more than VILBA_MAX_KEYFRAMES (256) key-frames in one window"
+                                                          : "invalid window";
             return VILBA_ERR_ARG;
         }
         max_K = std::max(max_K, meta[i].K), max_nf = std::max(max_nf, meta[i].n_free), max_ni = std::max(max_ni, meta[i].NI);
@@ -711,23 +716,25 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     }
     ctx->dims = choose_dims(ctx, n_win, max_ni, max_K, max_nf);
     // arena: [inputs of all windows | outputs of all windows | LmState array | work regions]
-    size_t in_o = 0, out_o = 0, wk_o = 0;
+    size_t in_o = 0, out_o = 0, chi_o = 0, wk_o = 0;
     for (int i = 0; i < n_win; ++i) {
         WinMeta& m = meta[i];
         m.L = make_layout(m, ctx->dims.point_grid, ctx->dims.sp_grid, std::max(1, ctx->dims.sp_tile_pts), ctx->comm != nullptr);
         m.in_base = in_o, in_o += m.L.in_bytes;
         m.out_base = out_o, out_o += m.L.out_bytes;
+        m.chi_base = chi_o, chi_o += m.L.chi_bytes;
         m.wk_base = wk_o, wk_o += m.L.wk_bytes;
     }
     const size_t lm_bytes = align_up(sizeof(LmState) * (size_t)n_win);
-    ctx->in_total = in_o, ctx->out_total = out_o;
+    ctx->in_total = in_o, ctx->out_small = out_o, ctx->out_total = out_o + chi_o;
     ctx->out_region = in_o;
-    ctx->lm_base = in_o + out_o;
+    ctx->lm_base = in_o + ctx->out_total;
     const size_t wk_region = ctx->lm_base + lm_bytes;
-    for (int i = 0; i < n_win; ++i) meta[i].out_base += ctx->out_region, meta[i].wk_base += wk_region;
+    for (int i = 0; i < n_win; ++i)
+        meta[i].out_base += ctx->out_region, meta[i].chi_base += ctx->out_region + out_o, meta[i].wk_base += wk_region;
     CK(ctx->arena.reserve(wk_region + wk_o), "cudaMalloc(arena)");
     CK(ctx->pinned.reserve(in_o), "cudaMallocHost(staging)");
-    CK(ctx->pinned_out.reserve(out_o + lm_bytes), "cudaMallocHost(results)");
+    CK(ctx->pinned_out.reserve(ctx->out_total + lm_bytes), "cudaMallocHost(results)");
     CK(ctx->pinned_small.reserve(sizeof(DevWindow) * (size_t)n_win + 256), "cudaMallocHost(desc)");
     char* h = ctx->pinned.base;
     char* d = ctx->arena.base;
@@ -956,7 +963,12 @@ int download_batch(vilba_ctx* ctx, vilba_result* out) {
     CK(launch_export(s, ctx->dwp, ctx->dims), "export");
     ctx->stats.kernel_launches += 1;
     char* hp = ctx->pinned_out.base;
-    CK(cudaMemcpyAsync(hp, ctx->arena.base + ctx->out_region, ctx->out_total, cudaMemcpyDeviceToHost, s), "D2H results");
+    // states, points and outlier flags of all windows always; the per-edge chi2 (2/3 of the bytes, nothing the reference's
+    // function hands back) only if some result asks for it
+    bool want_chi2 = false;
+    for (int i = 0; i < ctx->n_win; ++i) want_chi2 = want_chi2 || out[i].obs_chi2 != nullptr;
+    CK(cudaMemcpyAsync(hp, ctx->arena.base + ctx->out_region, want_chi2 ? ctx->out_total : ctx->out_small, cudaMemcpyDeviceToHost, s),
+       "D2H results");
     CK(cudaStreamSynchronize(s), "sync");
     parallel_for(ctx->n_win, host_thread_budget(ctx->batch_total_hint > ctx->n_win ? ctx->n_lanes : 1), [&](int i) {
         const WinMeta& m = ctx->meta[i];
@@ -964,7 +976,7 @@ int download_batch(vilba_ctx* ctx, vilba_result* out) {
         vilba_result& o = out[i];
         if (o.kf_state) std::memcpy(o.kf_state, src + m.L.o_kf, sizeof(double) * 22 * (size_t)m.K);
         if (o.pt_xyz && m.P) std::memcpy(o.pt_xyz, src + m.L.o_pts, sizeof(double) * 3 * (size_t)m.P);
-        if (o.obs_chi2 && m.E) std::memcpy(o.obs_chi2, src + m.L.o_chi2, sizeof(double) * (size_t)m.E);
+        if (o.obs_chi2 && m.E) std::memcpy(o.obs_chi2, hp + (m.chi_base - ctx->out_region), sizeof(double) * (size_t)m.E);
         if (o.obs_outlier && m.E) std::memcpy(o.obs_outlier, src + m.L.o_outlier, (size_t)m.E);
     });
     return VILBA_OK;

@@ -679,13 +679,13 @@ public:
             win.Pbc[r] = Tbc[4 * r + 3];
             win.gravity[r] = GravityVec[r];
         }
-        std::vector<double> out_state(kf_state.size()), out_pts(pt_xyz.size()), out_chi2(obs_kf.size());
+        std::vector<double> out_state(kf_state.size()), out_pts(pt_xyz.size());  // (no per-edge chi2: phase F does not read it)
         std::vector<uint8_t> out_outlier(obs_kf.size());
         vilba_result local_res;
         vilba_result& res = pTrace ? *pTrace : local_res;
         std::memset(&res, 0, sizeof(res));
         res.kf_state = out_state.data(), res.pt_xyz = out_pts.data();
-        res.obs_outlier = out_outlier.data(), res.obs_chi2 = out_chi2.data();
+        res.obs_outlier = out_outlier.data();
 
         // ---- phases C..E on the GPU ----
         static_assert(sizeof(bool) == 1, "bool* pbStopFlag is polled as a byte");
