@@ -394,3 +394,49 @@ def test_context_on_the_second_device(vilba, oracle):
         _compare(c.local_ba(wins[1]), refs[1], wins[1])
     finally:
         c.close()
+
+
+def test_full_c5_share_in_one_call(ctx, oracle, vilba):
+    """BASELINE config 5 at full size for one GPU: 64 independent C3 windows through ONE vilba_local_ba_batch call (four
+    concurrent lanes of 16).  Size-independent properties instead of 64 oracle solves: every window's result is what the
+    same window gives when it is solved alone (same LM decisions, states to round-off), the order of the windows in the
+    batch does not matter, results do not leak between windows (distinct windows -> distinct results); two windows
+    are also checked against the oracle."""
+    wins = [synth.make_config("c3", window_index=i) for i in range(64)]
+    res = ctx.local_ba_batch(wins)
+    assert all(r.status == 0 and len(r.trace) == 15 and r.stage2_ran == 1 for r in res)
+    alone = vilba.Context(0)
+    try:
+        for i in (0, 17, 40, 63):
+            a = alone.local_ba(wins[i])
+            assert [(t["trials"], t["accepted"], t["n_active_edges"]) for t in a.trace] == \
+                   [(t["trials"], t["accepted"], t["n_active_edges"]) for t in res[i].trace]
+            assert np.abs(a.kf_state - res[i].kf_state).max() < 1e-9 and np.abs(a.pt_xyz - res[i].pt_xyz).max() < 1e-9
+            assert np.array_equal(a.obs_outlier, res[i].obs_outlier)
+    finally:
+        alone.close()
+    for i in (5, 58):
+        _compare(res[i], oracle.local_ba(wins[i]), wins[i])
+    perm = np.random.default_rng(3).permutation(64)
+    res_p = ctx.local_ba_batch([wins[j] for j in perm])
+    for k, j in enumerate(perm[:16]):
+        assert np.abs(res_p[k].kf_state - res[j].kf_state).max() < 1e-9
+        assert np.array_equal(res_p[k].obs_outlier, res[j].obs_outlier)
+    finals = {round(r.trace[-1]["chi2_final"], 6) for r in res}
+    assert len(finals) == 64
+
+
+def test_solving_the_solution_again_changes_nothing_much(ctx):
+    """Idempotence of the solve as a whole: started from its own result, the two-stage schedule ends at a cost that is not
+    higher than where the first solve stopped its robust stage, and moves the key-frames by far less than the first solve."""
+    w = synth.make_config("c1")
+    r1 = ctx.local_ba(w)
+    w2 = synth.make_config("c1")
+    w2.kf_state = r1.kf_state.copy()
+    w2.pt_xyz = r1.pt_xyz.astype(np.float32).astype(np.float64)  # the shim hands points back as float32
+    r2 = ctx.local_ba(w2)
+    free = (w.kf_flags & capi.KF_FIXED) == 0
+    moved1 = np.abs(r1.kf_state[free, 0:3] - w.kf_state[free, 0:3]).max()
+    moved2 = np.abs(r2.kf_state[free, 0:3] - w2.kf_state[free, 0:3]).max()
+    assert moved2 < 0.1 * moved1 + 1e-4
+    assert r2.trace[0]["chi2_initial"] <= 1.05 * r1.trace[4]["chi2_final"]
