@@ -843,8 +843,12 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
     }
     std::vector<int> first_trace(ctx->n_win);
     for (int i = 0; i < ctx->n_win; ++i) first_trace[i] = lm[i].n_trace;
-    // one trial per iteration when every step is accepted, plus spares for rejected trials
-    int slots = iterations + (ctx->n_win > 1 ? 3 : 1);
+    // one trial per iteration when every step is accepted.  A single window gets one blind spare slot (a rejected trial then
+    // costs no host round trip; an unused slot is ~30 us of early-exit launches); a batch gets none: idle slots of one lane
+    // cost the other lanes' kernels their SMs (measured: 0 / 1 / 2 / 3 spares = 41.4 / 41.1 / 41.1 / 40.8 k LM iterations/s),
+    // and while a lane waits for the host the others run
+    static const int spare_env = std::getenv("VILBA_SPARE_SLOTS") ? std::max(0, std::atoi(std::getenv("VILBA_SPARE_SLOTS"))) : -1;
+    int slots = iterations + (spare_env >= 0 ? spare_env : (ctx->n_win > 1 ? 0 : 1));
     // every slot runs at least one trial of every unfinished window, so (iterations + 1) * max_trials slots always suffice
     const int max_rounds = 2 + ((iterations + 1) * std::max(1, ctx->prm.max_trials)) / 2;
     bool done = false;
