@@ -138,7 +138,7 @@ struct DevWindow {
     double* chi_partial;     // 2 * point_grid: per-CTA partial sums of chi2 and the landmark part of the gain scale
     unsigned* chi_counter;   // CTAs of update_eval that have delivered their partial
     long long* dbg;  // optional debug counters (16 x int64), may be null
-    int dbg_flags;   // timing-ablation switches (only honoured by -DVILBA_CHOL_TIMING builds)
+    int dbg_flags;   // timing-ablation switches of the Schur tile kernels (env VILBA_TS_ABLATE; only honoured by -DVILBA_TS_ABLATE builds)
     // calibration (g2otypes.h:686-705)
     double fx, fy, cx, cy;
     double Rcb[9];  // Rbc^T

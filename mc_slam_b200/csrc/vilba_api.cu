@@ -548,7 +548,7 @@ void fill_dev_window(const vilba_ctx* ctx, const vilba_window* w, const WinMeta&
     dw.dbg = reinterpret_cast<long long*>(wk + L.dbg);
     dw.chi_partial = reinterpret_cast<double*>(wk + L.chi_partial);
     dw.chi_counter = reinterpret_cast<unsigned*>(wk + L.chi_counter);
-    if (const char* e = std::getenv("VILBA_CHOL_ABLATE")) dw.dbg_flags = std::atoi(e);
+    if (const char* e = std::getenv("VILBA_TS_ABLATE")) dw.dbg_flags = std::atoi(e);
     dw.fx = w->fx, dw.fy = w->fy, dw.cx = w->cx, dw.cy = w->cy;
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) dw.Rcb[3 * r + c] = w->Rbc[3 * c + r];  // Rcb = Rbc^T
