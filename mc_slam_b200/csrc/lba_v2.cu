@@ -1236,7 +1236,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
     // ---- one LM trial (skipped unless phase == TRIAL) ----
     if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
     if (d.sp_warps > 0) {
-        schur_rec_kernel<<<dim3(d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_tile_pts, d.sp_mma);
+        schur_rec_kernel<<<dim3(4 * d.reduce_grid, d.n_windows), 256, 0, s>>>(wp, d.sp_tile_pts, d.sp_mma);
         if (d.sp_mma)
             schur_mma_kernel<<<dim3(d.sp_grid * d.sp_sets, d.n_windows), 32 * d.sp_warps, d.smem_sp, s>>>(wp, d.sp_sets, d.sp_tile_pts,
                                                                                                       d.sp_tile_edges);
