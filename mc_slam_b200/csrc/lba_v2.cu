@@ -1149,15 +1149,51 @@ __global__ void __launch_bounds__(256) schur_finish_pair_kernel(const DevWindow*
     }
 }
 
-// S = H_pp + lambda I - sum of the CTA partials (fixed order), b_s = b_p - sum; upper triangle only
+// S = H_pp + lambda I - sum of the CTA partials (fixed order), b_s = b_p - sum; upper triangle only.
+// Only the [P,Phi] x [P,Phi] entries of a block pair (36 of 225) and 6 of 15 rhs entries carry a landmark term: four
+// lanes share the partial sums of one such entry (lane k adds the point subsets k, k + 4, ... in order, then
+// (l0 + l1) + (l2 + l3): a fixed tree), every other entry is a copy.  (One thread per entry of S looping over all
+// point subsets took 29 us for a single window with 74 subsets -- longer than the tile kernel that produced them.)
 __global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __restrict__ wp, int point_ctas) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
     if (w.lm->phase != PH_TRIAL) return;
     const int n = w.n, nf = w.n_free;
     const double lambda = w.lm->lambda;
     const size_t accN = sp_acc_doubles(nf);
+    const size_t pairsN = (size_t)w.n_pairs * 36;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    // ---- entries with a landmark term: accumulator entry j -> (row, column) of S, or a rhs entry ----
+    const int sub = threadIdx.x & 3;
+    const int quad = (threadIdx.x & 31) >> 2;  // the four lanes of an entry are neighbours; a warp takes 8 entries per trip
+    for (size_t j0 = (tid >> 2) - quad; j0 < accN; j0 += nthreads >> 2) {  // (warp-uniform trip count: shuffles inside)
+        const size_t j = j0 + quad;
+        const bool valid = j < accN;
+        double sum = 0.0;
+        if (valid)
+            for (int c = sub; c < point_ctas; c += 4) sum += w.schur_partial[(size_t)c * accN + j];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (sub || !valid) continue;
+        if (j < pairsN) {
+            const int pair = (int)(j / 36), e = (int)(j - 36 * (size_t)pair), pr = e / 6, pc = e - 6 * pr;
+            int a = 0, off = 0;  // pair -> (a, b): pairs of row a start at a nf - a (a - 1) / 2
+            while (a + 1 < nf && off + (nf - a) <= pair) off += nf - a, ++a;
+            const int b = a + (pair - off);
+            const int gr = 15 * a + (pr < 3 ? pr : pr + 3), gc = 15 * b + (pc < 3 ? pc : pc + 3);
+            if (gr > gc) continue;  // lower part of a diagonal block
+            double v = w.Hpp[(size_t)gr * n + gc];
+            if (gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
+            w.S_w[(size_t)gr * w.lds + gc] = v - sum;
+        } else {
+            const int e = (int)(j - pairsN), a = e / 6, pr = e - 6 * a;
+            const int gr = 15 * a + (pr < 3 ? pr : pr + 3);
+            w.bs_w[gr] = w.bp[gr] - sum;
+        }
+    }
+    // ---- every other entry of the upper triangle and of the rhs: H_pp + lambda I, b_p ----
     const size_t total = (size_t)n * n + n;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t i = tid; i < total; i += nthreads) {
         const bool is_rhs = i >= (size_t)n * n;
         int gr, gc;
         if (is_rhs) {
@@ -1167,21 +1203,16 @@ __global__ void __launch_bounds__(256) schur_finish_kernel(const DevWindow* __re
             gc = (int)(i - (size_t)gr * n);
             if (gr > gc) continue;
         }
-        const int a = gr / 15, b = gc / 15, rr = gr - 15 * a, cc = gc - 15 * b;
+        const int rr = gr % 15, cc = gc % 15;
         const int pr = pose6_index(rr), pc = pose6_index(cc);
-        double v = is_rhs ? w.bp[gr] : w.Hpp[(size_t)gr * n + gc];  // (a sharded rank: its own partial sums)
-        if (!is_rhs && gr == gc && w.shard_owner) v += lambda;  // setLambda on the pose blocks (block_solver.hpp:570-577)
-        if (pr >= 0 && (is_rhs || pc >= 0)) {
-            const size_t off = is_rhs ? (size_t)(nf * (nf + 1) / 2) * 36 + 6 * a + pr
-                                      : (size_t)(a * nf - a * (a - 1) / 2 + (b - a)) * 36 + 6 * pr + pc;
-            double sum = 0.0;
-            for (int c = 0; c < point_ctas; ++c) sum += w.schur_partial[(size_t)c * accN + off];
-            v -= sum;
-        }
-        if (is_rhs)
-            w.bs_w[gr] = v;
-        else
+        if (pr >= 0 && (is_rhs || pc >= 0)) continue;  // done above
+        if (is_rhs) {
+            w.bs_w[gr] = w.bp[gr];
+        } else {
+            double v = w.Hpp[(size_t)gr * n + gc];
+            if (gr == gc && w.shard_owner) v += lambda;
             w.S_w[(size_t)gr * w.lds + gc] = v;
+        }
     }
 }
 
