@@ -28,6 +28,67 @@ __device__ __forceinline__ double group8_sum(double v) {
     return v;
 }
 
+// The LM decision of one trial (OptimizationAlgorithmLevenberg::solve, :120-160, and the loop condition of optimize(),
+// sparse_optimizer.cpp:376): one warp.  Runs at the tail of update_eval (the last CTA to arrive has chi2 and the landmark
+// part of the gain scale in hand), or as its own kernel behind the allreduce when the window is sharded.
+__device__ __forceinline__ void lm_decide_warp(const DevWindow& w, LmState* s, int lane) {
+    const double lambda = s->lambda;
+    double sc = 0.0;  // computeScale over the pose part (:182-189); landmarks arrive in scale_acc
+    if (!w.sharded)   // (sharded: shard_scale_kernel added it to scale_acc before the reduction, b_p is a partial sum here)
+        for (int j = lane; j < w.n; j += 32) sc += w.x[j] * (lambda * w.x[j] + w.bp[j]);
+    sc = warp_sum(sc);
+    if (lane == 0) {
+        double scale = sc + s->scale_acc;
+        scale += 1e-3;
+        double tempChi = s->chi_acc;
+        if (s->chol_fail) tempChi = DBL_MAX;
+        double rho = (s->current_chi - tempChi) / scale;
+        s->temp_chi = tempChi;
+        if (rho > 0 && isfinite(tempChi)) {  // :134-142
+            double alpha = 1. - pow((2 * rho - 1), 3.0);
+            alpha = fmin(alpha, w.lm_good_hi);
+            const double scaleFactor = fmax(w.lm_good_lo, alpha);
+            s->lambda = lambda * scaleFactor;
+            s->ni = 2;
+            s->current_chi = tempChi;
+            s->cur ^= 1;  // discardTop: the trial buffer becomes the estimate
+            s->accepted = 1;
+        } else {  // :143-147  pop: the estimate buffer is untouched, cached errors stay stale
+            s->lambda = lambda * s->ni;
+            s->ni *= 2;
+            s->accepted = 0;
+        }
+        s->rho = rho;
+        s->qmax += 1;
+        s->chi_acc = 0.0;
+        s->scale_acc = 0.0;
+        s->chol_fail = 0;
+        const bool again = (rho < 0) && (s->qmax < w.max_trials) && !s->stop;
+        if (!again) {
+            int res = 0;
+            if (s->qmax == w.max_trials || rho == 0)
+                res = 1;
+            else {
+                if ((s->ini_chi - s->current_chi) * 1e3 < s->ini_chi)
+                    s->n_bad++;
+                else
+                    s->n_bad = 0;
+                if (s->n_bad >= 3) res = 1;
+            }
+            s->iter_result = res;
+            if (s->n_trace < VILBA_MAX_TRACE) {
+                IterRec& r = s->trace[s->n_trace++];
+                r.stage = s->stage, r.iteration = s->iter, r.trials = s->qmax, r.result = res;
+                r.n_active = s->n_active, r.accepted = s->accepted;
+                r.chi0 = s->ini_chi, r.chi1 = s->current_chi, r.lambda = s->lambda, r.lambda_first = s->lambda_first;
+            }
+            s->iter += 1;
+            // optimize(): for (i < iterations && !terminate() && ok)   (sparse_optimizer.cpp:376)
+            s->phase = (res != 0 || s->iter >= s->max_iters || s->stop) ? PH_DONE : PH_LINEARIZE;
+        }
+    }
+}
+
 template <bool APPLY>
 __global__ void __launch_bounds__(kPointThreads, 2) update_eval_kernel(const DevWindow* __restrict__ wp) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
@@ -167,6 +228,10 @@ __global__ void __launch_bounds__(kPointThreads, 2) update_eval_kernel(const Dev
             if (APPLY) w.lm->scale_acc = s;
             *w.chi_counter = 0u;
         }
+        if (APPLY && !w.sharded) {  // every other CTA of this launch is past its work: the phase may change now
+            __syncwarp();
+            lm_decide_warp(w, w.lm, lane);
+        }
     }
 }
 
@@ -279,62 +344,8 @@ __global__ void __launch_bounds__(256) lm_iter_begin_kernel(const DevWindow* __r
 __global__ void __launch_bounds__(32) lm_decide_kernel(const DevWindow* __restrict__ wp) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
     LmState* s = w.lm;
-    if (s->phase != PH_TRIAL) return;
-    const double lambda = s->lambda;
-    double sc = 0.0;  // computeScale over the pose part (:182-189); landmarks arrive in scale_acc
-    if (!w.sharded)   // (sharded: shard_scale_kernel added it to scale_acc before the reduction, b_p is a partial sum here)
-        for (int j = threadIdx.x; j < w.n; j += 32) sc += w.x[j] * (lambda * w.x[j] + w.bp[j]);
-    sc = warp_sum(sc);
-    if (threadIdx.x == 0) {
-        double scale = sc + s->scale_acc;
-        scale += 1e-3;
-        double tempChi = s->chi_acc;
-        if (s->chol_fail) tempChi = DBL_MAX;
-        double rho = (s->current_chi - tempChi) / scale;
-        s->temp_chi = tempChi;
-        if (rho > 0 && isfinite(tempChi)) {  // :134-142
-            double alpha = 1. - pow((2 * rho - 1), 3.0);
-            alpha = fmin(alpha, w.lm_good_hi);
-            const double scaleFactor = fmax(w.lm_good_lo, alpha);
-            s->lambda = lambda * scaleFactor;
-            s->ni = 2;
-            s->current_chi = tempChi;
-            s->cur ^= 1;  // discardTop: the trial buffer becomes the estimate
-            s->accepted = 1;
-        } else {  // :143-147  pop: the estimate buffer is untouched, cached errors stay stale
-            s->lambda = lambda * s->ni;
-            s->ni *= 2;
-            s->accepted = 0;
-        }
-        s->rho = rho;
-        s->qmax += 1;
-        s->chi_acc = 0.0;
-        s->scale_acc = 0.0;
-        s->chol_fail = 0;
-        const bool again = (rho < 0) && (s->qmax < w.max_trials) && !s->stop;
-        if (!again) {
-            int res = 0;
-            if (s->qmax == w.max_trials || rho == 0)
-                res = 1;
-            else {
-                if ((s->ini_chi - s->current_chi) * 1e3 < s->ini_chi)
-                    s->n_bad++;
-                else
-                    s->n_bad = 0;
-                if (s->n_bad >= 3) res = 1;
-            }
-            s->iter_result = res;
-            if (s->n_trace < VILBA_MAX_TRACE) {
-                IterRec& r = s->trace[s->n_trace++];
-                r.stage = s->stage, r.iteration = s->iter, r.trials = s->qmax, r.result = res;
-                r.n_active = s->n_active, r.accepted = s->accepted;
-                r.chi0 = s->ini_chi, r.chi1 = s->current_chi, r.lambda = s->lambda, r.lambda_first = s->lambda_first;
-            }
-            s->iter += 1;
-            // optimize(): for (i < iterations && !terminate() && ok)   (sparse_optimizer.cpp:376)
-            s->phase = (res != 0 || s->iter >= s->max_iters || s->stop) ? PH_DONE : PH_LINEARIZE;
-        }
-    }
+    if (s->phase != PH_TRIAL || !w.sharded) return;  // (not sharded: decided at the tail of update_eval)
+    lm_decide_warp(w, s, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1297,7 +1297,8 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
         if ((e = comm->reduce(comm->self, RED_CHI, s)) != cudaSuccess) return e;
     }
     if (probe && (e = cudaEventRecord(probe[5], s)) != cudaSuccess) return e;
-    if ((e = launch_lm_decide(s, wp, d)) != cudaSuccess) return e;
+    // the LM decision: at the tail of update_eval, or (sharded) its own kernel behind the reduction of chi2 | scale
+    if (comm && (e = launch_lm_decide(s, wp, d)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

@@ -858,7 +858,7 @@ int run_stage(vilba_ctx* ctx, int stage, int iterations, vilba_result* out, cons
                 CK(cudaGraphLaunch(exec, s), "graph launch");
             else
                 CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, ctx->dims, probe_take(ctx), comm), "slot");
-            stt.kernel_launches += kernels_per_slot(ctx->dims);
+            stt.kernel_launches += kernels_per_slot(ctx->dims, comm != nullptr);
         }
         int r = read_lm(ctx, lm, stop_flag);
         if (r != VILBA_OK) return r;
