@@ -243,12 +243,12 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
 cudaError_t launch_build_pair_lists(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_cull(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
 cudaError_t launch_final_flags(cudaStream_t s, const DevWindow* wp, const LaunchDims& d);
-// kernels one slot launches (for vilba_stats::kernel_launches): 6 common (+ 3 when sharded: decide, diag, scale) + Schur
+// kernels one slot launches (for vilba_stats::kernel_launches): 5 common (+ 4 when sharded: iter_begin, decide, diag, scale) + Schur
 // (2 gather / 3 tile scan) + Cholesky
 inline int kernels_per_slot(const LaunchDims& d, bool sharded = false) {
     const int schur = d.sp_warps > 0 ? 3 : 2;
     const int chol = d.chol_big_tiles > 0 ? 3 * d.chol_big_tiles : 1;  // diag + panel + update per step (last update replaced by the back substitution)
-    return 6 + (sharded ? 3 : 0) + schur + chol;
+    return 5 + (sharded ? 4 : 0) + schur + chol;
 }
 
 }  // namespace vilba

@@ -151,6 +151,42 @@ __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, doub
     atomicMax(addr, (unsigned long long)__double_as_longlong(v));  // order-preserving for v >= 0
 }
 
+// Start of an LM iteration behind the linearisation (one CTA of 256 threads): computeLambdaInit at iteration 0
+// (optimization_algorithm_levenberg.cpp:166-180: tau * max |diag H|), the per-iteration bookkeeping of solve() (:61-80),
+// phase LINEARIZE -> TRIAL.  Runs at the tail of assemble_hpp (last CTA to arrive), or as its own kernel behind the
+// reduction of diag H when the window is sharded.
+__device__ __forceinline__ void lm_iter_begin_cta(const DevWindow& w, LmState* s) {
+    __shared__ double red[8];
+    const int iteration = s->iter;
+    double m = 0.0;
+    if (iteration == 0) {
+        if (w.sharded)  // diag(H_pp) summed over the ranks | every rank's max |diag H_ll| (RED_DIAG)
+            for (int d = threadIdx.x; d < w.n + w.shard_world; d += blockDim.x) m = fmax(m, fabs(w.diag_red[d]));
+        else
+            for (int d = threadIdx.x; d < w.n; d += blockDim.x) m = fmax(m, fabs(__ldcg(w.Hpp + (size_t)d * w.n + d)));
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (iteration == 0) {  // computeLambdaInit (optimization_algorithm_levenberg.cpp:166-180)
+            double mx = w.sharded ? 0.0 : __longlong_as_double((long long)s->maxdiag_bits);
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, red[i]);
+            s->lambda = w.lm_tau * mx;
+            s->ni = 2.0;
+            s->n_bad = 0;
+        }
+        s->ini_chi = s->current_chi;
+        s->lambda_first = s->lambda;
+        s->qmax = 0;
+        s->iter_result = -1;
+        s->maxdiag_bits = 0ull;
+        s->chi_acc = 0.0;
+        s->scale_acc = 0.0;
+        s->phase = PH_TRIAL;
+    }
+}
+
 // ---- bulk asynchronous copies global -> shared memory (TMA, cp.async.bulk) completing on an mbarrier ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {

@@ -309,36 +309,8 @@ __global__ void lm_stage_begin_kernel(const DevWindow* __restrict__ wp, int stag
 __global__ void __launch_bounds__(256) lm_iter_begin_kernel(const DevWindow* __restrict__ wp) {
     const DevWindow w = wp[blockIdx.y];  // one window per grid row
     LmState* s = w.lm;
-    if (s->phase != PH_LINEARIZE) return;
-    __shared__ double red[8];
-    const int iteration = s->iter;
-    double m = 0.0;
-    if (iteration == 0) {
-        if (w.sharded)  // diag(H_pp) summed over the ranks | every rank's max |diag H_ll| (RED_DIAG)
-            for (int d = threadIdx.x; d < w.n + w.shard_world; d += blockDim.x) m = fmax(m, fabs(w.diag_red[d]));
-        else
-            for (int d = threadIdx.x; d < w.n; d += blockDim.x) m = fmax(m, fabs(w.Hpp[(size_t)d * w.n + d]));
-    }
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (iteration == 0) {  // computeLambdaInit (optimization_algorithm_levenberg.cpp:166-180)
-            double mx = w.sharded ? 0.0 : __longlong_as_double((long long)s->maxdiag_bits);
-            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, red[i]);
-            s->lambda = w.lm_tau * mx;
-            s->ni = 2.0;
-            s->n_bad = 0;
-        }
-        s->ini_chi = s->current_chi;
-        s->lambda_first = s->lambda;
-        s->qmax = 0;
-        s->iter_result = -1;
-        s->maxdiag_bits = 0ull;
-        s->chi_acc = 0.0;
-        s->scale_acc = 0.0;
-        s->phase = PH_TRIAL;
-    }
+    if (s->phase != PH_LINEARIZE || !w.sharded) return;  // (not sharded: done at the tail of assemble_hpp)
+    lm_iter_begin_cta(w, s);
 }
 
 __global__ void __launch_bounds__(32) lm_decide_kernel(const DevWindow* __restrict__ wp) {
@@ -434,7 +406,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const DevWindow* __restrict_
     }
     int* lm = reinterpret_cast<int*>(w.lm);
     for (int i = tid; i < (int)(sizeof(LmState) / sizeof(int)); i += nt) lm[i] = 0;
-    if (tid == 0) *w.chi_counter = 0u;
+    if (tid == 0) w.chi_counter[0] = w.chi_counter[1] = 0u;  // arrival counters of update_eval / assemble_hpp
 }
 
 __global__ void __launch_bounds__(256) export_kernel(const DevWindow* __restrict__ wp) {

@@ -400,6 +400,20 @@ __global__ void __launch_bounds__(256) assemble_hpp_kernel(const DevWindow* __re
         else
             w.Hpp_w[i] = v;
     }
+    if (w.sharded) return;  // diag H crosses the ranks first: lm_iter_begin_kernel behind the reduction
+    // the last CTA to arrive starts the LM iteration (H_pp is complete then): no kernel of its own for a few loads
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(w.chi_counter + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x == 0) w.chi_counter[1] = 0u;
+        lm_iter_begin_cta(w, w.lm);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1263,7 +1277,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
         if ((e = comm->reduce(comm->self, RED_DIAG, s)) != cudaSuccess) return e;
     }
     if (probe && (e = cudaEventRecord(probe[1], s)) != cudaSuccess) return e;
-    if ((e = launch_lm_iter_begin(s, wp, d)) != cudaSuccess) return e;
+    if (comm && (e = launch_lm_iter_begin(s, wp, d)) != cudaSuccess) return e;  // (not sharded: tail of assemble_hpp)
     // ---- one LM trial (skipped unless phase == TRIAL) ----
     if (probe && (e = cudaEventRecord(probe[2], s)) != cudaSuccess) return e;
     if (d.sp_warps > 0) {
