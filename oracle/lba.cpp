@@ -843,7 +843,7 @@ int oracle_debug_system(const vilba_window* win, const vilba_params* params, int
 }
 
 const char* oracle_build_info(void) {
-    return "vilba CPU oracle (dependency-free restatement of the reference g2o path; SO3/pre-integration pinned against the compiled reference, g2o part unpinned) "
+    return "vilba CPU oracle (dependency-free restatement of the reference g2o path; SO3 / pre-integration / NavState / the three factors pinned against the compiled reference; g2o's optimiser restated) "
 #ifdef __VERSION__
            "gcc " __VERSION__
 #endif

@@ -1,5 +1,5 @@
-"""ctypes binding of oracle/_ref/libref_imu.so: the reference's OWN so3 / IMUPreintegrator / NavState / imudata sources
-compiled unmodified against oracle/eigen_stub (oracle/Makefile target `ref`).  TEST INFRASTRUCTURE: the pin of the
+"""ctypes binding of oracle/_ref/libref_imu.so: the reference's OWN so3 / IMUPreintegrator / NavState / imudata / g2otypes
+sources compiled unmodified against oracle/eigen_stub and oracle/g2o_stub (oracle/Makefile target `ref`).  TEST INFRASTRUCTURE: the pin of the
 oracle's restatement; only tests/ and the golden-vector generators use it."""
 from __future__ import annotations
 
@@ -42,6 +42,15 @@ def lib() -> C.CDLL:
             f.argtypes = [_dp] * n
             f.restype = None
         l.ref_build_info.restype = C.c_char_p
+        l.ref_edge_pvr.argtypes = [C.c_int32] + [_dp] * 13
+        l.ref_edge_pvr.restype = None
+        l.ref_edge_bias.argtypes = [_dp] * 5
+        l.ref_edge_bias.restype = None
+        l.ref_edge_mono.argtypes = [_dp] * 7 + [C.POINTER(C.c_int32)]
+        l.ref_edge_mono.restype = None
+        for name in ("ref_vertex_pvr_oplus", "ref_vertex_bias_oplus"):
+            getattr(l, name).argtypes = [_dp, _dp]
+            getattr(l, name).restype = None
         _lib = l
     return _lib
 
@@ -103,3 +112,39 @@ def inc_bias(ns, d):
 
 def imu_constants(): return _call("ref_imu_constants", 4)
 def build_info() -> str: return lib().ref_build_info().decode()
+
+
+# ---- the reference's own factor classes (src/IMU/g2otypes.cpp), see oracle/ref_harness_edges.cpp ----
+def edge_pvr(gyro, acc, dt, bg, ba, ns_i, ns_j, ns_bias_i, g):
+    """EdgeNavStatePVR with the pre-integration of the given samples as measurement: (err 9, Ji 9x9, Jj 9x9, Jb 9x6)."""
+    gy, ac, t = _a(gyro), _a(acc), _a(dt)
+    err, Ji, Jj, Jb = np.zeros(9), np.zeros(81), np.zeros(81), np.zeros(54)
+    lib().ref_edge_pvr(t.size, _d(gy), _d(ac), _d(t), _d(_a(bg, 3)), _d(_a(ba, 3)), _d(_a(ns_i, 22)), _d(_a(ns_j, 22)),
+                       _d(_a(ns_bias_i, 22)), _d(_a(g, 3)), _d(err), _d(Ji), _d(Jj), _d(Jb))
+    return err, Ji.reshape(9, 9), Jj.reshape(9, 9), Jb.reshape(9, 6)
+
+
+def edge_bias(ns_i, ns_j):
+    err, Ji, Jj = np.zeros(6), np.zeros(36), np.zeros(36)
+    lib().ref_edge_bias(_d(_a(ns_i, 22)), _d(_a(ns_j, 22)), _d(err), _d(Ji), _d(Jj))
+    return err, Ji.reshape(6, 6), Jj.reshape(6, 6)
+
+
+def edge_mono(ns, pw, calib, uv):
+    """EdgeNavStatePVRPointXYZ: (err 2, Jpoint 2x3, Jpvr 2x9, isDepthPositive)."""
+    err, Jp, Jn = np.zeros(2), np.zeros(6), np.zeros(18)
+    dp = C.c_int32(0)
+    lib().ref_edge_mono(_d(_a(ns, 22)), _d(_a(pw, 3)), _d(_a(calib, 16)), _d(_a(uv, 2)), _d(err), _d(Jp), _d(Jn), C.byref(dp))
+    return err, Jp.reshape(2, 3), Jn.reshape(2, 9), bool(dp.value)
+
+
+def vertex_pvr_oplus(ns, d):
+    s = _a(ns, 22).copy()
+    lib().ref_vertex_pvr_oplus(_d(s), _d(_a(d, 9)))
+    return s
+
+
+def vertex_bias_oplus(ns, d):
+    s = _a(ns, 22).copy()
+    lib().ref_vertex_bias_oplus(_d(s), _d(_a(d, 6)))
+    return s

@@ -109,6 +109,6 @@ void ref_imu_constants(double out[4]) {
     out[3] = IMUData::getAccBiasRW2();
 }
 const char* ref_build_info(void) {
-    return "unmodified /root/reference/src/IMU/{so3,IMUPreintegrator,NavState,imudata}.cpp + oracle/eigen_stub";
+    return "unmodified /root/reference/src/IMU/{so3,IMUPreintegrator,NavState,imudata,g2otypes}.cpp + oracle/eigen_stub + oracle/g2o_stub";
 }
 }

@@ -4,11 +4,14 @@
  * for Optimizer::LocalBundleAdjustmentNavState and IMUPreintegrator::update.  It is the checker
  * for tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never
  * the product.  PARITY PARTLY PINNED: the reference ships no tests / golden vectors for this path.
- * SO3, IMUPreintegrator, NavState and the IMU constants are pinned against the reference's OWN sources,
- * compiled unmodified against a minimal Eigen stand-in (oracle/Makefile target `ref`, oracle/_ref/,
- * tests/test_oracle_vs_ref.py, tests/golden/ref_imu_v1.npz).  The g2o machinery, src/IMU/g2otypes.cpp
- * and src/Optimizer.cpp cannot be compiled here (all of g2o + Eigen + OpenCV + CHOLMOD) and stay
- * RESTATED AND UNPINNED against executed reference code; see DESIGN.md section 2.
+ * Pinned against the reference's OWN sources, compiled unmodified and EXECUTED (oracle/Makefile target `ref`,
+ * oracle/_ref/; Eigen replaced by the minimal stand-in oracle/eigen_stub, the four g2o base-class headers
+ * by oracle/g2o_stub): SO3, IMUPreintegrator, NavState, the IMU constants (tests/test_oracle_vs_ref.py,
+ * tests/golden/ref_imu_v1.npz) and the three factors with their Jacobians plus the vertex updates of
+ * src/IMU/g2otypes.cpp (tests/test_oracle_edges_vs_ref.py, tests/golden/ref_edges_v1.npz).
+ * RESTATED AND NOT PINNED BY EXECUTION: g2o's optimiser (block solver, Schur complement, Levenberg-
+ * Marquardt, robust kernel; Thirdparty/g2o needs Eigen proper) and the driver in src/Optimizer.cpp
+ * (needs g2o + OpenCV + CHOLMOD); see DESIGN.md section 2.
  */
 #ifndef VILBA_ORACLE_H
 #define VILBA_ORACLE_H

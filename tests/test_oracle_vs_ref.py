@@ -5,8 +5,9 @@ reference's public methods).  A line of oracle/preint.h or oracle/so3.h that dri
 so3.cpp:87-300 fails here.  Where neither the compiled reference nor the reference tree exists (the GPU box), the same
 comparisons run against tests/golden/ref_imu_v1.npz, which was produced by that library (tests/golden/make_ref_golden.py).
 
-NOT pinned this way: g2o, src/IMU/g2otypes.cpp and src/Optimizer.cpp need all of g2o + OpenCV + CHOLMOD to compile and
-stay restated (pinned by numeric Jacobians and the independent dense LM driver)."""
+The three factors of src/IMU/g2otypes.cpp are pinned the same way in tests/test_oracle_edges_vs_ref.py.  NOT pinned by
+execution: g2o's optimiser and src/Optimizer.cpp (they need Eigen proper + OpenCV + CHOLMOD) stay restated, pinned by the
+independent dense LM driver and the properties in tests/test_oracle_solver.py; see DESIGN.md section 2."""
 import os
 
 import numpy as np
