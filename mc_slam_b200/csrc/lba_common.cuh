@@ -82,9 +82,10 @@ __device__ __forceinline__ MonoObs load_obs(const int4* obs, int e) {
     return o;
 }
 
-// RobustKernelHuber::robustify (robust_kernel_impl.cpp:78-91)
+// RobustKernelHuber::robustify (robust_kernel_impl.cpp:78-91); delta^2 lives in a float member of the reference's kernel
+// (robust_kernel_impl.h:84), so it is rounded to single precision here too
 __device__ __forceinline__ void huber(double e, double delta, double& rho0, double& rho1) {
-    const double dsqr = delta * delta;
+    const double dsqr = (double)(float)(delta * delta);
     if (e <= dsqr) {
         rho0 = e;
         rho1 = 1.0;

@@ -53,9 +53,11 @@ struct NavState {
     }
 };
 
-// RobustKernelHuber::robustify (robust_kernel_impl.cpp:78-91); dsqr = delta*delta (:65-69)
+// RobustKernelHuber::robustify (robust_kernel_impl.cpp:78-91).  dsqr = delta * delta is set by setDelta (:65-69) into a
+// FLOAT member in this g2o (robust_kernel_impl.h:84: `float dsqr;`), so the inlier test and rho(e) see delta^2 rounded to
+// single precision -- found by executing the reference's kernel (tests/test_oracle_lm_vs_ref.py::test_huber_kernel).
 inline void huber(double e, double delta, double rho[3]) {
-    const double dsqr = delta * delta;
+    const double dsqr = (double)(float)(delta * delta);
     if (e <= dsqr) {
         rho[0] = e;
         rho[1] = 1.;

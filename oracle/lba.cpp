@@ -796,6 +796,8 @@ void oracle_bias_edge(const double ns_i[22], const double ns_j[22], double err[6
     bias_error(si, sj).store(err);
 }
 
+void oracle_huber(double e2, double delta, double rho[3]) { huber(e2, delta, rho); }
+
 int oracle_debug_system(const vilba_window* win, const vilba_params* params, int robust_mono, double lambda,
                         double* Hpp, double* bp, double* Hll, double* bl, double* Hpl, double* S, double* bs,
                         double* x, double* chi2, double* obs_chi2) {
@@ -843,7 +845,7 @@ int oracle_debug_system(const vilba_window* win, const vilba_params* params, int
 }
 
 const char* oracle_build_info(void) {
-    return "vilba CPU oracle (dependency-free restatement of the reference g2o path; SO3 / pre-integration / NavState / the three factors pinned against the compiled reference; g2o's optimiser restated) "
+    return "vilba CPU oracle (dependency-free restatement of the reference g2o path; SO3 / pre-integration / NavState / the three factors / the LM step / the Huber kernel pinned against the compiled reference; g2o's block solver restated) "
 #ifdef __VERSION__
            "gcc " __VERSION__
 #endif

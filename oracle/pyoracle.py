@@ -171,6 +171,15 @@ def bias_edge(ns_i, ns_j):
     return err
 
 
+def huber(e2: float, delta: float) -> np.ndarray:
+    rho = np.zeros(3)
+    f = lib().oracle_huber
+    f.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double)]
+    f.restype = None
+    f(float(e2), float(delta), rho.ctypes.data_as(C.POINTER(C.c_double)))
+    return rho
+
+
 def debug_system(win: Window, lam: float, robust_mono: bool = True, params: Optional[Params] = None) -> dict:
     n = 15 * win.n_free
     P, E = win.n_pts, win.n_obs

@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
         l.ref_edge_bias.restype = None
         l.ref_edge_mono.argtypes = [_dp] * 7 + [C.POINTER(C.c_int32)]
         l.ref_edge_mono.restype = None
+        l.ref_huber.argtypes = [C.c_double, C.c_double, _dp]
+        l.ref_huber.restype = None
         for name in ("ref_vertex_pvr_oplus", "ref_vertex_bias_oplus"):
             getattr(l, name).argtypes = [_dp, _dp]
             getattr(l, name).restype = None
@@ -148,3 +150,28 @@ def vertex_bias_oplus(ns, d):
     s = _a(ns, 22).copy()
     lib().ref_vertex_bias_oplus(_d(s), _d(_a(d, 6)))
     return s
+
+
+# ---- g2o's own Levenberg-Marquardt step and robust kernel, see oracle/ref_harness_lm.cpp ----
+def huber(e2: float, delta: float) -> np.ndarray:
+    """RobustKernelHuber::robustify after setDelta(delta): rho, rho', rho''."""
+    rho = np.zeros(3)
+    lib().ref_huber(float(e2), float(delta), _d(rho))
+    return rho
+
+
+def lm_local_ba(win, params=None, stop_flag=None):
+    """oracle_local_ba with the reference's OptimizationAlgorithmLevenberg::solve() as the LM step."""
+    from mc_slam_b200.capi import CResult, CWindow, Params, Result, default_params
+    f = lib().ref_lm_local_ba
+    f.argtypes = [C.POINTER(CWindow), C.POINTER(Params), C.POINTER(CResult), C.POINTER(C.c_uint8)]
+    f.restype = C.c_int
+    res = Result.alloc(win)
+    cw, cr = win.as_c(), res.as_c()
+    p = params or default_params()
+    sf = stop_flag.ctypes.data_as(C.POINTER(C.c_uint8)) if stop_flag is not None else None
+    st = f(C.byref(cw), C.byref(p), C.byref(cr), sf)
+    res.take(cr)
+    if st < 0:
+        raise RuntimeError(f"ref_lm_local_ba failed with status {st}")
+    return res

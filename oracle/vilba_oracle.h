@@ -8,10 +8,13 @@
  * oracle/_ref/; Eigen replaced by the minimal stand-in oracle/eigen_stub, the four g2o base-class headers
  * by oracle/g2o_stub): SO3, IMUPreintegrator, NavState, the IMU constants (tests/test_oracle_vs_ref.py,
  * tests/golden/ref_imu_v1.npz) and the three factors with their Jacobians plus the vertex updates of
- * src/IMU/g2otypes.cpp (tests/test_oracle_edges_vs_ref.py, tests/golden/ref_edges_v1.npz).
- * RESTATED AND NOT PINNED BY EXECUTION: g2o's optimiser (block solver, Schur complement, Levenberg-
- * Marquardt, robust kernel; Thirdparty/g2o needs Eigen proper) and the driver in src/Optimizer.cpp
- * (needs g2o + OpenCV + CHOLMOD); see DESIGN.md section 2.
+ * src/IMU/g2otypes.cpp (tests/test_oracle_edges_vs_ref.py, tests/golden/ref_edges_v1.npz); g2o's Levenberg-
+ * Marquardt step (optimization_algorithm_levenberg.cpp) and Huber kernel (robust_kernel_impl.cpp), compiled
+ * unmodified with oracle/g2o_lm_stub around them and run on the oracle's linear algebra
+ * (oracle/ref_harness_lm.cpp, tests/test_oracle_lm_vs_ref.py).
+ * RESTATED AND NOT PINNED BY EXECUTION: g2o's BlockSolver (buildSystem, Schur complement, linear solve:
+ * needs Eigen proper), the loop of SparseOptimizer::optimize and the driver in src/Optimizer.cpp (needs
+ * g2o + OpenCV + CHOLMOD); see DESIGN.md section 2.
  */
 #ifndef VILBA_ORACLE_H
 #define VILBA_ORACLE_H
@@ -49,6 +52,8 @@ void oracle_pvr_edge(const double ns_i[22], const double ns_j[22], const double 
                      const double preint[142], const double g[3], double err[9], double Ji[81],
                      double Jj[81], double Jb[54]);
 void oracle_bias_edge(const double ns_i[22], const double ns_j[22], double err[6]);
+/* RobustKernelHuber::robustify with setDelta(delta): rho, rho', rho'' */
+void oracle_huber(double e2, double delta, double rho[3]);
 
 /* Builds the normal equations at the window's initial state exactly like BlockSolver::buildSystem
  * and performs ONE Schur solve with the given lambda (block_solver.hpp:354-486).  Output sizes:

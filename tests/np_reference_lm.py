@@ -18,7 +18,7 @@ from mc_slam_b200 import capi
 
 
 def _huber(e, delta):
-    d2 = delta * delta
+    d2 = float(np.float32(delta * delta))  # `float dsqr;` in the reference's kernel (robust_kernel_impl.h:84)
     if e <= d2:
         return e, 1.0
     s = np.sqrt(e)
