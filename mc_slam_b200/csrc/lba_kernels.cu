@@ -7,7 +7,9 @@
 //   imu_prepare : information matrix of EdgeNavStatePVR (src/Optimizer.cpp:2510)
 //   lm_*        : OptimizationAlgorithmLevenberg::solve bookkeeping (optimization_algorithm_levenberg.cpp:61-164)
 //                 and the iteration loop of SparseOptimizer::optimize (sparse_optimizer.cpp:376-414), kept in
-//                 device memory so that the host never synchronises inside an optimize() call
+//                 device memory so that the host never synchronises inside an optimize() call.  The accept / reject
+//                 decision runs in the last CTA of update_eval (lm_decide_warp), the start of an iteration in the last
+//                 CTA of assemble_hpp; a sharded window keeps both as kernels behind its reductions
 //   flags       : the cull / outlier loops of Optimizer::LocalBundleAdjustmentNavState (Optimizer.cpp:2659-2701)
 // The accumulation kernels (linearize / assemble / Schur) live in lba_v2.cu, the reduced-system LDL^T in chol_la.cu / chol_big.cu.
 //

@@ -8,7 +8,11 @@
 //                  with itself), reduced per CTA in a fixed order and written as one partial per CTA;
 //                  every IMU edge pair writes its own 30x30 slot.  IMU CTAs run in the same launch.
 //   assemble_hpp : H_pp / b_p = fixed-order sum of the CTA partials and the IMU slots
-//                  (BlockSolver::buildSystem's flush, g2o/core/block_solver.hpp:547-557).
+//                  (BlockSolver::buildSystem's flush, g2o/core/block_solver.hpp:547-557); its last CTA to arrive starts
+//                  the LM iteration (lambda init, bookkeeping: lm_iter_begin_cta).
+//   schur_rec / schur_tile / schur_finish : the same landmark loop for windows of <= 32 key-frames as a TILE SCAN over
+//                  the map points (TMA bulk copies, key-frame masks, no pair lists); options: one lane per block pair,
+//                  one FP64 MMA per hit.  See the comments above each kernel.
 //   schur_gather : S(a,b) = H_pp(a,b) + lambda I - sum_l W_a,l D_l^-1 W_b,l^T as a GATHER over precomputed
 //                  (edge_a, edge_b) lists per key-frame block pair, one CTA per block pair, register
 //                  accumulation, fixed reduction tree -- replaces 6.5 M FP64 atomics per LM trial
