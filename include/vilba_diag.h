@@ -27,6 +27,18 @@ int vilba_diag_dense_solve(int32_t device, int32_t n, const double* S, const dou
 /* 1 if variant / cluster can handle a system of dimension n (shared-memory capacity), else 0 */
 int vilba_diag_dense_supported(int32_t n, int32_t variant, int32_t cluster);
 
+/* The normal equations of the FIRST Levenberg-Marquardt trial of a window, as the kernels leave them in device memory:
+ * upload, initial evaluation, linearise + accumulate (what BlockSolver::buildSystem produces: H_pp, b_p, H_ll, b_l, the
+ * H_pl blocks) and the Schur step with the initial lambda (block_solver.hpp:381-439: S = H_pp + lambda I - sum W D^-1 W^T,
+ * b_s); the reduced solve is not run.  For tests: the same quantities come out of the oracle for the same lambda.
+ *   Hpp n*n (row-major, upper triangle filled), bp n, Hll n_pts*6 (xx xy xz yy yz zz), bl n_pts*3,
+ *   W n_obs*18 (6x3 blocks, rows [P, Phi]; zero for observations of fixed key-frames), S n*n (upper triangle), bs n;
+ *   n = 15 * (free key-frames).  Any output pointer may be NULL.  `ctx` is a vilba_ctx from vilba_create. */
+struct vilba_ctx;
+struct vilba_window;
+int vilba_diag_first_trial(struct vilba_ctx* ctx, const struct vilba_window* win, double* lambda_out, double* Hpp, double* bp,
+                           double* Hll, double* bl, double* W, double* S, double* bs);
+
 #ifdef __cplusplus
 }
 #endif

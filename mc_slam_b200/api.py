@@ -75,6 +75,18 @@ class Context:
         self._check(st, "vilba_global_ba")
         return res.take(cr)
 
+    # ---- diagnostics (include/vilba_diag.h): the normal equations of the first LM trial ----------
+    def first_trial_system(self, win: Window) -> dict:
+        n, P, E = 15 * win.n_free, win.n_pts, win.n_obs
+        o = dict(lam=np.zeros(1), Hpp=np.zeros((n, n)), bp=np.zeros(n), Hll=np.zeros((P, 6)), bl=np.zeros((P, 3)),
+                 W=np.zeros((E, 6, 3)), S=np.zeros((n, n)), bs=np.zeros(n))
+        cw = win.as_c()
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        st = self._lib.vilba_diag_first_trial(self._h, C.byref(cw), *[dp(o[k]) for k in ("lam", "Hpp", "bp", "Hll", "bl", "W", "S", "bs")])
+        self._check(st, "vilba_diag_first_trial")
+        o["lam"] = float(o["lam"][0])
+        return o
+
     def local_ba_batch(self, wins: Sequence[Window]) -> List[Result]:
         n = len(wins)
         results = [Result.alloc(w) for w in wins]

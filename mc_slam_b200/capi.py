@@ -389,7 +389,8 @@ EXPORTED_SYMBOLS = [  # every symbol include/vilba.h declares
     "vilba_reset_stats",
     "vilba_set_profiling",
 ]
-DIAG_SYMBOLS = [  # every symbol include/vilba_diag.h declares (diagnostics, not the reference boundary)
+DIAG_SYMBOLS = [
+    "vilba_diag_first_trial",  # every symbol include/vilba_diag.h declares (diagnostics, not the reference boundary)
     "vilba_diag_dense_solve",
     "vilba_diag_dense_supported",
 ]
@@ -476,6 +477,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         _c_int32_p, _c_double_p,
     ]
     lib.vilba_diag_dense_solve.restype = C.c_int
+    lib.vilba_diag_first_trial.argtypes = [C.c_void_p, C.POINTER(CWindow)] + [_c_double_p] * 8
+    lib.vilba_diag_first_trial.restype = C.c_int
     lib.vilba_diag_dense_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.vilba_diag_dense_supported.restype = C.c_int
     if path is None:

@@ -204,6 +204,7 @@ struct LaunchDims {
     size_t smem_lin;      // ... of linearize_v2
     int lin_threads;      // threads per CTA of linearize_v2: fewer warps (= fewer private accumulators) for many free key-frames
     size_t smem_sp;       // ... of schur_tile
+    int dbg_stop_after_schur;  // diagnostics only (vilba_diag_first_trial): the slot ends behind the Schur step, S | b_s intact
 };
 size_t point_smem_bytes(int K);
 size_t linearize_smem_bytes(int K, int n_free, int threads);

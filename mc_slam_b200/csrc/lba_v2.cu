@@ -1304,6 +1304,7 @@ cudaError_t launch_slot(cudaStream_t s, cudaStream_t side, cudaEvent_t fork, cud
         schur_gather_kernel<<<dim3(d.gather_grid, d.n_windows), kSchurThreads, 0, s>>>(wp);
     }
     if (comm && (e = comm->reduce(comm->self, RED_S, s)) != cudaSuccess) return e;  // S | b_s = sum of the partial reduced systems
+    if (d.dbg_stop_after_schur) return cudaGetLastError();
     if (probe && (e = cudaEventRecord(probe[3], s)) != cudaSuccess) return e;
     if (d.chol_big_tiles > 0) e = launch_chol_big(s, side, fork, join, wp, d);
     else e = launch_chol_la(s, wp, d.n_windows, d.chol_cluster, d.chol_n);

@@ -1472,6 +1472,44 @@ int vilba_preintegrate_batch(vilba_ctx* ctx, int32_t n_pairs, const int32_t* sam
     return VILBA_OK;
 }
 
+// include/vilba_diag.h: the normal equations of the first LM trial, straight from the device buffers
+int vilba_diag_first_trial(vilba_ctx* ctx, const vilba_window* win, double* lambda_out, double* Hpp, double* bp, double* Hll,
+                           double* bl, double* W, double* S, double* bs) {
+    if (!ctx || !win || ctx->comm) return VILBA_ERR_ARG;
+    ctx->split = 0;
+    int r = upload_batch(ctx, 1, win);
+    if (r != VILBA_OK) return r;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = ctx->stream;
+    CK(launch_reset(s, ctx->dwp, ctx->dims), "reset");
+    CK(launch_imu_prepare(s, ctx->dwp, ctx->dims), "imu_prepare");
+    CK(launch_eval_initial(s, ctx->dwp, ctx->dims), "eval");
+    CK(launch_stage_begin(s, ctx->dwp, ctx->dims, 1, 1), "stage_begin");
+    LaunchDims d = ctx->dims;
+    d.dbg_stop_after_schur = 1;
+    CK(launch_slot(s, ctx->stream2, ctx->ev_fork, ctx->ev_join, ctx->dwp, d, nullptr, nullptr), "slot");
+    CK(cudaStreamSynchronize(s), "sync");
+    const DevWindow& dw = ctx->dw[0];
+    const WinMeta& m = ctx->meta[0];
+    const size_t n = (size_t)m.n;
+    LmState lm;
+    CK(cudaMemcpy(&lm, dw.lm, sizeof(lm), cudaMemcpyDeviceToHost), "D2H lm");
+    if (lambda_out) *lambda_out = lm.lambda_first;
+    auto get = [&](double* dst, const double* src, size_t count) {
+        return !dst || !count || cudaMemcpy(dst, src, sizeof(double) * count, cudaMemcpyDeviceToHost) == cudaSuccess;
+    };
+    bool ok = get(Hpp, dw.Hpp, n * n) && get(bp, dw.bp, n) && get(Hll, dw.Hll, 6 * (size_t)m.P) && get(bl, dw.bl, 3 * (size_t)m.P) &&
+              get(W, dw.W, 18 * (size_t)m.E) && get(bs, dw.bs, n);
+    if (ok && S && n)
+        ok = cudaMemcpy2D(S, sizeof(double) * n, dw.S, sizeof(double) * (size_t)dw.lds, sizeof(double) * n, n,
+                          cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (!ok) {
+        ctx->err = "vilba_diag_first_trial: copy failed";
+        return VILBA_ERR_CUDA;
+    }
+    return VILBA_OK;
+}
+
 void vilba_get_stats(const vilba_ctx* ctx, vilba_stats* s) {
     if (ctx && s) *s = ctx->stats;
 }
