@@ -199,8 +199,8 @@ def config_of(w, name, nw):
 
 def run_reference(args, rank, world):
     """CPU arm: the dependency-free restatement of the reference's g2o path (the reference itself cannot be
-    compiled here: Eigen/OpenCV/CHOLMOD are absent; its SO3 / pre-integration part is pinned against the compiled
-    reference, tests/test_oracle_vs_ref.py), on all host threads the workload can use: one window per thread (each
+    compiled here as a whole: Eigen/OpenCV/CHOLMOD are absent; its pre-integration, factors, LM step and Huber kernel are
+    pinned against the compiled reference sources, tests/test_oracle_*vs_ref.py), on all host threads the workload can use: one window per thread (each
     optimisation is single-threaded like the reference's).  One step = one window solve on every thread: a bounded
     sample of the workload (a 20-KF window is ~0.3 s on one core)."""
     if rank != 0:
