@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -229,6 +230,8 @@ struct vilba_ctx {
     cudaEvent_t start_after = nullptr;   // lane: event of the parent stream the solve starts after
     cudaEvent_t ev_done = nullptr;       // lane: recorded behind the last kernel of a solve
     std::vector<vilba_ctx*> lanes;  // sub-contexts the windows of a large batch are split over
+    std::mutex upload_mx;           // lanes flatten + enqueue their H2D one after the other, each with all host threads
+    bool upload_exclusive = false;  // (set on a lane while it holds the parent's upload_mx)
     int n_lanes = 4;                // env VILBA_BATCH_LANES
     std::vector<cudaEvent_t> probes;  // 8 events per profiled slot
     size_t probes_used = 0;
@@ -651,7 +654,7 @@ int upload_batch(vilba_ctx* ctx, int n_win, const vilba_window* wins) {
     std::vector<WinMeta>& meta = ctx->meta;
     meta.assign(n_win, WinMeta());
     std::vector<int> status(n_win, VILBA_OK);
-    const int host_threads = host_thread_budget(ctx->batch_total_hint > n_win ? ctx->n_lanes : 1);
+    const int host_threads = host_thread_budget(ctx->batch_total_hint > n_win && !ctx->upload_exclusive ? ctx->n_lanes : 1);
     parallel_for(n_win, host_threads, [&](int i) {
         const vilba_window* w = &wins[i];
         int st = check_window(w);
@@ -1391,7 +1394,16 @@ int vilba_local_ba_batch(vilba_ctx* ctx, int32_t n_windows, const vilba_window* 
                     vilba_ctx* c = ctx->lanes[l];
                     c->batch_total_hint = nb;
                     const int f = b + first[l], n = first[l + 1] - first[l];
-                    int q = upload_batch(c, n, win + f);
+                    // Staggered start: the lanes flatten their windows one after the other, each with the whole host thread
+                    // budget, so the first lane's kernels run while the others still pack (all lanes packing side by side
+                    // with a quarter of the threads each kept the GPU idle until the last one was done)
+                    int q;
+                    {
+                        std::lock_guard<std::mutex> lock(ctx->upload_mx);
+                        c->upload_exclusive = true;
+                        q = upload_batch(c, n, win + f);
+                        c->upload_exclusive = false;
+                    }
                     if (q == VILBA_OK) q = solve_batch(c, out + f, nullptr);
                     if (q == VILBA_OK) q = download_batch(c, out + f);
                     return q;
